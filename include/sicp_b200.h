@@ -1,0 +1,181 @@
+/*
+ * sicp_b200.h — C ABI of libsicp_b200.so: the B200 (sm_100a) ICP inner loop behind the
+ * simpleICP Python API.
+ *
+ * The reference (pglira/simpleICP) has no FFI/plugin layer; its boundary is the
+ * Python class surface exported at python/simpleicp/__init__.py:12-14.  This header is the
+ * C boundary a binding of that surface needs: one entry point per reference method on the hot
+ * path, each citing the reference code it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch / C++ types.
+ *  - Every function returns a sicp_status; sicp_last_error(ctx) gives the message.
+ *  - Pointers marked [h|d] may be host or device memory (detected with
+ *    cudaPointerGetAttributes); [h] must be host memory.  The caller owns every buffer it passes
+ *    and allocates every output; the library never frees or keeps caller memory.
+ *  - All point arrays are row-major n x 3 float64 (NumPy's layout for PointCloud.X,
+ *    python/simpleicp/pointcloud.py:81-84).  Indices are int64 like NumPy's.
+ *  - A context is bound to one device and one CUDA stream (e.g. torch's current stream); calls
+ *    on one context are not thread-safe, different contexts are independent.
+ *  - Angles are radians at this boundary (the Python facade converts degrees,
+ *    python/simpleicp/simpleicp.py:146-148).
+ */
+#ifndef SICP_B200_H
+#define SICP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SICP_ABI_VERSION 1
+
+typedef enum {
+  SICP_OK = 0,
+  SICP_ERR_BAD_ARG = 1,       /* argument checks, simpleicp.py:326-353, pointcloud.py:158-159   */
+  SICP_ERR_NO_OVERLAP = 2,    /* "Point clouds do not overlap ...", simpleicp.py:165-170         */
+  SICP_ERR_TOO_FEW_CORR = 3,  /* "Too few correspondences!" (< 6), simpleicp.py:209-214          */
+  SICP_ERR_CUDA = 4,
+  SICP_ERR_SINGULAR = 5,      /* normal equations not positive definite                          */
+  SICP_ERR_STATE = 6          /* call order violated (e.g. match before set_clouds)              */
+} sicp_status;
+
+typedef struct sicp_ctx sicp_ctx;
+
+/* Nearest-neighbour engine selection (both engines are exact). */
+typedef enum {
+  SICP_NN_AUTO = 0,  /* uniform-grid search, TMA brute force for queries the grid cannot bound */
+  SICP_NN_GRID = 1,  /* grid only, ring expansion until proven exact                           */
+  SICP_NN_BRUTE = 2  /* TMA-staged tiled brute force for every query                           */
+} sicp_nn_engine;
+
+/* Normal sign convention.  The reference's sign is whatever LAPACK dgeev returns
+ * (pointcloud.py:191-197, np.linalg.eig) — see DESIGN.md "normal sign". */
+typedef enum {
+  SICP_SIGN_DGEEV = 0,     /* reproduce np.linalg.eig's sign (Hessenberg-QR path of dgeev)       */
+  SICP_SIGN_CANONICAL = 1  /* largest-magnitude component positive                              */
+} sicp_sign_mode;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+int32_t sicp_abi_version(void);
+int32_t sicp_create(int32_t device, void* cuda_stream, sicp_ctx** out);
+int32_t sicp_destroy(sicp_ctx* ctx);
+const char* sicp_last_error(sicp_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value);
+/*  keys: "nn_engine" (sicp_nn_engine), "sign_mode" (sicp_sign_mode), "grid_target_occupancy",
+ *        "grid_max_rings", "host_sync_every" (iterations between host stop-rule reads)         */
+
+/* ---- clouds: SimpleICP.add_point_clouds (simpleicp.py:58-73) + PointCloud.X ---------------- */
+int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz /*[h|d] n_fix x 3*/, int64_t n_fix,
+                        const double* mov_xyz /*[h|d] n_mov x 3*/, int64_t n_mov);
+
+/* ---- selection: PointCloud.idx_selected / select_n_points (pointcloud.py:91-147) ----------- */
+/* idx ascending fixed-cloud indices; idx == NULL selects all n_fix points.                    */
+int32_t sicp_set_selected(sicp_ctx* ctx, const int64_t* idx /*[h|d] K or NULL*/, int64_t K);
+
+/* PointCloud.select_in_range (pointcloud.py:149-171) as used at simpleicp.py:158-170:
+ * keep[i] = 1 iff the nearest point of H0 * X_mov to selected fixed point i is STRICTLY closer
+ * than max_range.  n_kept == 0 returns SICP_ERR_NO_OVERLAP.                                    */
+int32_t sicp_select_in_range(sicp_ctx* ctx, const double H0[16], double max_range,
+                             uint8_t* keep /*[h|d] K*/, int64_t* n_kept /*[h]*/);
+
+/* ---- normals: PointCloud.estimate_normals (pointcloud.py:173-203) ---------------------------
+ * k-NN (self included) in the fixed cloud, covariance (ddof=1), symmetric 3x3 eigen-solve;
+ * normal = eigenvector of the smallest eigenvalue, planarity = (l_mid - l_min) / l_max, float32.
+ * Outputs may be NULL (kept on the device for sicp_match either way).                          */
+int32_t sicp_estimate_normals(sicp_ctx* ctx, int32_t neighbors, float* nx, float* ny, float* nz,
+                              float* planarity /*[h|d] K each*/);
+/* The reference's "columns already present" hook (simpleicp.py:176-178).                       */
+int32_t sicp_set_normals(sicp_ctx* ctx, const float* nx, const float* ny, const float* nz,
+                         const float* planarity /*[h|d] K each*/);
+/* neighbour indices of the last sicp_estimate_normals (test/inspection hook), K x neighbors.   */
+int32_t sicp_get_knn(sicp_ctx* ctx, int64_t* idx /*[h|d] K x k*/, double* dist2 /*[h|d] or NULL*/);
+
+/* ---- one ICP iteration, stage by stage ------------------------------------------------------ */
+/* CorrPts.match (corrpts.py:124-137, 195-211): pc2_idx[i] = argmin_j |H x_mov_j - x_fix_sel_i|,
+ * dist[i] = (H x_mov_pc2idx - x_fix_sel_i) . n_i.                                              */
+int32_t sicp_match(sicp_ctx* ctx, const double H[16], int64_t* pc2_idx /*[h|d] K or NULL*/,
+                   double* dist /*[h|d] K or NULL*/);
+
+/* CorrPts.reject_wrt_planarity + reject_wrt_point_to_plane_distances (corrpts.py:139-188):
+ * (double)planarity_f32 >= min_planarity (NaN drops), then |d - median| <= 3 * MAD with the
+ * RAW median absolute deviation (SciPy scale=1.0, corrpts.py:186).
+ * stats[4] = {median, mad, mean(d kept), popstd(d kept)}.                                      */
+int32_t sicp_reject(sicp_ctx* ctx, double min_planarity, uint8_t* keep /*[h|d] K or NULL*/,
+                    int64_t* n_kept /*[h]*/, double stats[4] /*[h] or NULL*/);
+
+typedef struct {
+  double x0[6];           /* start values alpha1..3 [rad], tx,ty,tz (simpleicp.py:223-227)       */
+  double observed[6];     /* rbp_observed_values, radians                                      */
+  double obs_weight[6];   /* rbp_observation_weights: 0 free, +inf fixed, else observed          */
+  double distance_weight; /* > 0; <= 0 or NaN means "None": 1/std(d kept)^2 (simpleicp.py:233)   */
+} sicp_lsq_params;
+
+/* SimpleICPOptimization.estimate_parameters (optimization.py:65-124): argmin over the free
+ * parameters of sum (w n.(R(x) p2 + t - p1))^2 + sum (w_j (x_j - obs_j))^2, solved to
+ * convergence (Levenberg-Marquardt on the exact Euler model).  residuals = unweighted signed
+ * distances at the solution, in kept order.  stats[2] = {mean, population std} of them.        */
+int32_t sicp_solve(sicp_ctx* ctx, const sicp_lsq_params* p, double x[6] /*[h]*/,
+                   double H[16] /*[h]*/, double* residuals /*[h|d] n_kept or NULL*/,
+                   double stats[2] /*[h] or NULL*/, double* distance_weight_used /*[h] or NULL*/);
+
+/* SimpleICPOptimization.estimate_parameter_uncertainties (optimization.py:126-170) for the last
+ * sicp_solve / sicp_run: sigma[j] = sqrt(Cxx_jj), NaN for fixed parameters.                     */
+int32_t sicp_uncertainties(sicp_ctx* ctx, double sigma[6] /*[h]*/);
+
+/* ---- the fused loop: SimpleICP.run iterations (simpleicp.py:184-281) ------------------------ */
+typedef struct {
+  double min_planarity;
+  double min_change;       /* percent, simpleicp.py:355-379                                     */
+  int32_t max_iterations;
+  int32_t reserved;
+  sicp_lsq_params lsq;     /* x0 = observed values on iteration 0, as the reference              */
+} sicp_run_params;
+
+typedef struct {
+  int64_t n_kept;
+  double median, mad;          /* of the planarity survivors                                    */
+  double mean_dist, std_dist;  /* kept distances before the solve ("orig:0" row on iteration 0)  */
+  double x[6];
+  double mean_res, std_res;    /* residuals after the solve (log row, stop rule)                */
+  double distance_weight;
+  int32_t lm_iterations;
+  int32_t n_bruteforce;        /* queries answered by the brute-force engine                    */
+} sicp_iter_record;
+
+typedef struct {
+  int32_t iterations;          /* number of iterations run (the reference's it + 1)             */
+  int32_t converged;           /* 1 if the stop rule fired, 0 if max_iterations was reached     */
+  double x[6];
+  double H[16];
+  double sigma[6];
+  int64_t n_residuals;
+  double loop_ms;              /* device time of the iteration loop (CUDA events)               */
+} sicp_run_result;
+
+int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out /*[h]*/,
+                 sicp_iter_record* log /*[h] max_iterations entries or NULL*/);
+/* residuals of the final iteration in kept order (simpleicp.py:324, 4th return value).          */
+int32_t sicp_get_residuals(sicp_ctx* ctx, double* residuals /*[h|d] cap*/, int64_t cap,
+                           int64_t* n /*[h]*/);
+
+/* One iteration (match + reject + solve) with no host round trip except the record; used by the
+ * benchmark to time the hot path in isolation.  x_in/out: cumulative parameters.              */
+int32_t sicp_iterate(sicp_ctx* ctx, const sicp_run_params* p, const double x_in[6],
+                     sicp_iter_record* rec /*[h] or NULL: fully asynchronous*/);
+
+/* ---- PointCloud.transform_by_H (pointcloud.py:205-217), final application simpleicp.py:316 -- */
+int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out /*[h|d] n_mov x 3*/);
+
+/* ---- device timing of the last call of each stage, milliseconds ---------------------------- */
+typedef struct {
+  double upload_ms, grid_mov_ms, grid_fix_ms, overlap_ms, normals_ms, match_ms, reject_solve_ms,
+      transform_ms;
+} sicp_timings;
+int32_t sicp_get_timings(sicp_ctx* ctx, sicp_timings* t /*[h]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SICP_B200_H */

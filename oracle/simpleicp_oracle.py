@@ -139,12 +139,12 @@ def match(
 def reject(
     d: np.ndarray, planarity_f32: np.ndarray, min_planarity: float
 ) -> Tuple[np.ndarray, float, float]:
-    """corrpts.py:139-163 then 165-188 — planarity mask first (float32 compare, NaN -> drop),
+    """corrpts.py:139-163 then 165-188 — planarity mask first (float32 values compared in float64, NaN -> drop),
     then |d - median| <= 3 * MAD on the survivors with MAD *unscaled* (SciPy default scale=1.0;
     corrpts.py:186).  Returns (keep mask over K, median, mad)."""
-    # same expression as corrpts.py:152-155: float32 array >= caller's scalar (NumPy decides the
-    # comparison type: float32 for a Python float under NEP 50)
-    keep1 = planarity_f32 >= min_planarity
+    # corrpts.py:152-155 compares `Sparse[float32].to_numpy() >= min_planarity`; pandas hands the
+    # sparse float32 column back as float64, so the comparison is a float64 one.
+    keep1 = planarity_f32.astype(np.float64) >= min_planarity
     ds = d[keep1]
     if ds.size == 0:
         return np.zeros_like(keep1), np.nan, np.nan

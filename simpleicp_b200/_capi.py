@@ -1,0 +1,333 @@
+"""ctypes binding of libsicp_b200.so (the C ABI declared in include/sicp_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that is impossible
+an ImportError is raised, and creating an Engine without a CUDA device raises SicpError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libsicp_b200.so"
+
+SICP_OK, SICP_ERR_BAD_ARG, SICP_ERR_NO_OVERLAP, SICP_ERR_TOO_FEW_CORR = 0, 1, 2, 3
+SICP_ERR_CUDA, SICP_ERR_SINGULAR, SICP_ERR_STATE = 4, 5, 6
+NN_AUTO, NN_GRID, NN_BRUTE = 0, 1, 2
+SIGN_DGEEV, SIGN_CANONICAL = 0, 1
+
+# every symbol include/sicp_b200.h declares (tests check the library exports all of them)
+SYMBOLS = (
+    "sicp_abi_version", "sicp_create", "sicp_destroy", "sicp_last_error", "sicp_set_option",
+    "sicp_set_clouds", "sicp_set_selected", "sicp_select_in_range", "sicp_estimate_normals",
+    "sicp_set_normals", "sicp_get_knn", "sicp_match", "sicp_reject", "sicp_solve",
+    "sicp_uncertainties", "sicp_run", "sicp_get_residuals", "sicp_iterate", "sicp_transform",
+    "sicp_get_timings",
+)
+
+
+class LsqParams(C.Structure):
+    _fields_ = [("x0", C.c_double * 6), ("observed", C.c_double * 6),
+                ("obs_weight", C.c_double * 6), ("distance_weight", C.c_double)]
+
+
+class RunParams(C.Structure):
+    _fields_ = [("min_planarity", C.c_double), ("min_change", C.c_double),
+                ("max_iterations", C.c_int32), ("reserved", C.c_int32), ("lsq", LsqParams)]
+
+
+class IterRecord(C.Structure):
+    _fields_ = [("n_kept", C.c_int64), ("median", C.c_double), ("mad", C.c_double),
+                ("mean_dist", C.c_double), ("std_dist", C.c_double), ("x", C.c_double * 6),
+                ("mean_res", C.c_double), ("std_res", C.c_double), ("distance_weight", C.c_double),
+                ("lm_iterations", C.c_int32), ("n_bruteforce", C.c_int32)]
+
+
+class RunResult(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("x", C.c_double * 6),
+                ("H", C.c_double * 16), ("sigma", C.c_double * 6), ("n_residuals", C.c_int64),
+                ("loop_ms", C.c_double)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("upload_ms", "grid_mov_ms", "grid_fix_ms", "overlap_ms",
+                                          "normals_ms", "match_ms", "reject_solve_ms",
+                                          "transform_ms")]
+
+
+class SicpError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libsicp_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """Load (building first if needed) the CUDA library.  Never falls back to a CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if not build_if_missing:
+            raise ImportError(f"{LIB_PATH} is missing; run `python -m simpleicp_b200._build`")
+        from . import _build
+
+        _build.build()
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.sicp_abi_version.restype = i32
+    lib.sicp_last_error.restype = C.c_char_p
+    lib.sicp_last_error.argtypes = [vp]
+    sigs = {
+        "sicp_create": [i32, vp, C.POINTER(vp)],
+        "sicp_destroy": [vp],
+        "sicp_set_option": [vp, C.c_char_p, dbl],
+        "sicp_set_clouds": [vp, vp, i64, vp, i64],
+        "sicp_set_selected": [vp, vp, i64],
+        "sicp_select_in_range": [vp, C.POINTER(dbl), dbl, vp, C.POINTER(i64)],
+        "sicp_estimate_normals": [vp, i32, vp, vp, vp, vp],
+        "sicp_set_normals": [vp, vp, vp, vp, vp],
+        "sicp_get_knn": [vp, vp, vp],
+        "sicp_match": [vp, C.POINTER(dbl), vp, vp],
+        "sicp_reject": [vp, dbl, vp, C.POINTER(i64), C.POINTER(dbl)],
+        "sicp_solve": [vp, C.POINTER(LsqParams), C.POINTER(dbl), C.POINTER(dbl), vp,
+                       C.POINTER(dbl), C.POINTER(dbl)],
+        "sicp_uncertainties": [vp, C.POINTER(dbl)],
+        "sicp_run": [vp, C.POINTER(RunParams), C.POINTER(RunResult), C.POINTER(IterRecord)],
+        "sicp_get_residuals": [vp, vp, i64, C.POINTER(i64)],
+        "sicp_iterate": [vp, C.POINTER(RunParams), C.POINTER(dbl), C.POINTER(IterRecord)],
+        "sicp_transform": [vp, C.POINTER(dbl), vp],
+        "sicp_get_timings": [vp, C.POINTER(Timings)],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def _ptr(a) -> Optional[int]:
+    """Raw address of a NumPy array or a torch tensor (host or CUDA); None passes NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+def _as_f64_xyz(X):
+    """(n,3) float64 C-contiguous view/copy of a NumPy array or torch tensor."""
+    if isinstance(X, np.ndarray) or not hasattr(X, "data_ptr"):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2 or X.shape[1] != 3:
+            raise ValueError("X must have 3 columns!")
+        return X
+    import torch
+
+    if X.dim() != 2 or X.shape[1] != 3:
+        raise ValueError("X must have 3 columns!")
+    return X.to(torch.float64).contiguous()
+
+
+def _d6(v: Sequence[float]):
+    return (C.c_double * 6)(*[float(x) for x in v])
+
+
+def _d16(H) -> "C.Array":
+    H = np.asarray(H, dtype=np.float64).reshape(16)
+    return (C.c_double * 16)(*H.tolist())
+
+
+def current_stream_ptr(device: int) -> int:
+    """torch's current CUDA stream on `device` (PyTorch owns streams and user-visible buffers);
+    the legacy default stream when torch is not importable."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_stream(device).cuda_stream)
+    except ImportError:
+        pass
+    return 0
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """Host output buffer in pinned memory (through torch) so D2H copies run at link speed."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            tdt = {np.float64: torch.float64, np.float32: torch.float32, np.int64: torch.int64,
+                   np.uint8: torch.uint8}[np.dtype(dtype).type]
+            return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+    except (ImportError, RuntimeError):
+        pass
+    return np.empty(shape, dtype=dtype)
+
+
+class Engine:
+    """Thin object wrapper over one sicp_ctx."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.device = device
+        st = current_stream_ptr(device) if stream is None else stream
+        rc = self._lib.sicp_create(device, C.c_void_p(st), C.byref(self._h))
+        if rc != SICP_OK:
+            msg = self._lib.sicp_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise SicpError(rc, msg)
+        self.n_fix = self.n_mov = self.K = 0
+
+    # -- plumbing
+    def _check(self, rc: int):
+        if rc != SICP_OK:
+            raise SicpError(rc, self._lib.sicp_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.sicp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, key: str, value: float):
+        self._check(self._lib.sicp_set_option(self._h, key.encode(), float(value)))
+
+    # -- stages
+    def set_clouds(self, X_fix, X_mov):
+        Xf, Xm = _as_f64_xyz(X_fix), _as_f64_xyz(X_mov)
+        self.n_fix, self.n_mov = int(Xf.shape[0]), int(Xm.shape[0])
+        self._check(self._lib.sicp_set_clouds(self._h, _ptr(Xf), self.n_fix, _ptr(Xm), self.n_mov))
+        self.K = 0
+
+    def set_selected(self, idx=None):
+        if idx is None:
+            self._check(self._lib.sicp_set_selected(self._h, None, self.n_fix))
+            self.K = self.n_fix
+        else:
+            idx = np.ascontiguousarray(idx, dtype=np.int64)
+            self._check(self._lib.sicp_set_selected(self._h, _ptr(idx), idx.size))
+            self.K = int(idx.size)
+
+    def select_in_range(self, H0, max_range: float) -> np.ndarray:
+        keep = np.empty(self.K, dtype=np.uint8)
+        n = C.c_int64(0)
+        self._check(self._lib.sicp_select_in_range(self._h, _d16(H0), float(max_range), _ptr(keep),
+                                                   C.byref(n)))
+        return keep.astype(bool)
+
+    def estimate_normals(self, neighbors: int):
+        out = np.empty((4, self.K), dtype=np.float32)
+        self._check(self._lib.sicp_estimate_normals(
+            self._h, int(neighbors), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,
+            out[3].ctypes.data))
+        return out[0], out[1], out[2], out[3]
+
+    def set_normals(self, nx, ny, nz, planarity):
+        a = [np.ascontiguousarray(v, dtype=np.float32) for v in (nx, ny, nz, planarity)]
+        for v in a:
+            if v.size != self.K:
+                raise ValueError("normal arrays must have one entry per selected point")
+        self._check(self._lib.sicp_set_normals(self._h, *[_ptr(v) for v in a]))
+
+    def get_knn(self, k: int):
+        idx = np.empty((self.K, k), dtype=np.int64)
+        d2 = np.empty((self.K, k), dtype=np.float64)
+        self._check(self._lib.sicp_get_knn(self._h, _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def match(self, H):
+        idx = np.empty(self.K, dtype=np.int64)
+        d = np.empty(self.K, dtype=np.float64)
+        self._check(self._lib.sicp_match(self._h, _d16(H), _ptr(idx), _ptr(d)))
+        return idx, d
+
+    def reject(self, min_planarity: float):
+        keep = np.empty(self.K, dtype=np.uint8)
+        n = C.c_int64(0)
+        stats = (C.c_double * 4)()
+        self._check(self._lib.sicp_reject(self._h, float(min_planarity), _ptr(keep), C.byref(n), stats))
+        return keep.astype(bool), int(n.value), list(stats)
+
+    @staticmethod
+    def lsq_params(x0, observed, obs_weight, distance_weight) -> LsqParams:
+        p = LsqParams()
+        p.x0 = _d6(x0)
+        p.observed = _d6(observed)
+        p.obs_weight = _d6(obs_weight)
+        p.distance_weight = float("nan") if distance_weight is None else float(distance_weight)
+        return p
+
+    def solve(self, x0, observed, obs_weight, distance_weight, n_kept: int):
+        p = self.lsq_params(x0, observed, obs_weight, distance_weight)
+        x = (C.c_double * 6)()
+        H = (C.c_double * 16)()
+        stats = (C.c_double * 2)()
+        w = C.c_double(0)
+        res = np.empty(n_kept, dtype=np.float64)
+        self._check(self._lib.sicp_solve(self._h, C.byref(p), x, H, _ptr(res), stats, C.byref(w)))
+        return np.array(x), np.array(H).reshape(4, 4), res, list(stats), float(w.value)
+
+    def uncertainties(self) -> np.ndarray:
+        s = (C.c_double * 6)()
+        self._check(self._lib.sicp_uncertainties(self._h, s))
+        return np.array(s)
+
+    @staticmethod
+    def run_params(min_planarity, min_change, max_iterations, lsq: LsqParams) -> RunParams:
+        p = RunParams()
+        p.min_planarity = float(min_planarity)
+        p.min_change = float(min_change)
+        p.max_iterations = int(max_iterations)
+        p.lsq = lsq
+        return p
+
+    def run(self, params: RunParams):
+        out = RunResult()
+        log = (IterRecord * int(params.max_iterations))()
+        self._check(self._lib.sicp_run(self._h, C.byref(params), C.byref(out), log))
+        n = C.c_int64(0)
+        res = np.empty(int(out.n_residuals), dtype=np.float64)
+        self._check(self._lib.sicp_get_residuals(self._h, _ptr(res), res.size, C.byref(n)))
+        return out, [log[i] for i in range(out.iterations)], res
+
+    def iterate(self, params: RunParams, x_in=None, want_record: bool = False):
+        rec = IterRecord() if want_record else None
+        self._check(self._lib.sicp_iterate(
+            self._h, C.byref(params), None if x_in is None else _d6(x_in),
+            C.byref(rec) if rec is not None else None))
+        return rec
+
+    def transform(self, H, out=None):
+        """X_mov transformed by H.  `out` may be a CUDA torch tensor (n_mov, 3) float64."""
+        if out is None:
+            out = pinned_empty((self.n_mov, 3), np.float64)
+        self._check(self._lib.sicp_transform(self._h, _d16(H), _ptr(out)))
+        return out
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self._lib.sicp_get_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in Timings._fields_}

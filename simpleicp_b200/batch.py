@@ -1,0 +1,103 @@
+"""Batched registration of independent (X_fix, X_mov) pairs, sharded over GPUs.
+
+Independent pairs share nothing: each rank registers its static share on its
+own GPU with the single-GPU pipeline and the only exchange is one all-gather of a fixed-size
+record per pair — H (16 f64), iterations, kept correspondences, mean and std of the final
+residuals — over NCCL (gloo on CPU-only hosts for the tests of the sharding logic).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+RECORD_LEN = 20  # H (16) + iterations + n_kept + mean + std
+
+
+def shard_pairs(n_pairs: int, world_size: int, rank: int) -> List[int]:
+    """Static round-robin assignment: pair i belongs to rank i % world_size."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("invalid rank / world_size")
+    return list(range(rank, n_pairs, world_size))
+
+
+def pack_record(H: np.ndarray, iterations: int, n_kept: int, mean: float, std: float) -> np.ndarray:
+    r = np.empty(RECORD_LEN)
+    r[:16] = np.asarray(H, dtype=float).reshape(16)
+    r[16:] = (iterations, n_kept, mean, std)
+    return r
+
+
+def gather_records(local: np.ndarray, n_pairs: int, world_size: int, rank: int, dist=None,
+                   device=None) -> np.ndarray:
+    """All-gather the per-pair records.  `local` is (len(shard), RECORD_LEN) in shard order;
+    returns (n_pairs, RECORD_LEN) in pair order on every rank."""
+    if world_size == 1 or dist is None:
+        out = np.zeros((n_pairs, RECORD_LEN))
+        out[shard_pairs(n_pairs, 1, 0)] = local
+        return out
+    import torch
+
+    per = (n_pairs + world_size - 1) // world_size  # equal-size slots, last ones may be padding
+    buf = torch.full((per, RECORD_LEN), float("nan"), dtype=torch.float64, device=device)
+    if local.shape[0]:
+        buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(buf.device)
+    gathered = torch.empty((world_size * per, RECORD_LEN), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(gathered, buf)
+    g = gathered.cpu().numpy().reshape(world_size, per, RECORD_LEN)
+    out = np.zeros((n_pairs, RECORD_LEN))
+    for r in range(world_size):
+        ids = shard_pairs(n_pairs, world_size, r)
+        out[ids] = g[r, : len(ids)]
+    return out
+
+
+def simpleicp_batch(
+    pairs: Sequence[Tuple[np.ndarray, np.ndarray]] | Callable[[int], Tuple[np.ndarray, np.ndarray]],
+    n_pairs: Optional[int] = None,
+    *,
+    rank: int = 0,
+    world_size: int = 1,
+    dist=None,
+    device: int = 0,
+    register_fn=None,
+    **run_kwargs,
+) -> np.ndarray:
+    """Register every pair; returns the (n_pairs, 20) record table on every rank.
+
+    `pairs` is a sequence or a generator function i -> (X_fix, X_mov) (so that ranks only
+    materialise their own share).  `register_fn` defaults to the GPU pipeline
+    (simpleicp_b200.register on cuda:`device`); tests inject a stub to exercise the sharding and
+    the collective on CPU.
+    """
+    if n_pairs is None:
+        n_pairs = len(pairs)  # type: ignore[arg-type]
+    get = pairs if callable(pairs) else (lambda i: pairs[i])  # type: ignore[index]
+    mine = shard_pairs(n_pairs, world_size, rank)
+    eng = None
+    if register_fn is None:
+        from . import _capi
+        from .simpleicp import register
+
+        eng = _capi.Engine(device)
+
+        def register_fn(Xf, Xm, **kw):  # noqa: E306
+            return register(Xf, Xm, engine=eng, **kw)
+
+    local = np.zeros((len(mine), RECORD_LEN))
+    try:
+        for j, i in enumerate(mine):
+            Xf, Xm = get(i)
+            res = register_fn(Xf, Xm, **run_kwargs)
+            last = res.records[res.iterations - 1]
+            local[j] = pack_record(res.H, res.iterations, last["n_kept"], last["mean_res"],
+                                   last["std_res"])
+    finally:
+        if eng is not None:
+            eng.close()
+    dev = None
+    if dist is not None and world_size > 1:
+        import torch
+
+        dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    return gather_records(local, n_pairs, world_size, rank, dist, dev)

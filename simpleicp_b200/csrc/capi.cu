@@ -1,0 +1,623 @@
+// capi.cu — the extern "C" boundary declared in include/sicp_b200.h.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "ctx.cuh"
+
+struct sicp_ctx {
+  sicp::Ctx c;
+  int it_counter = 0;
+};
+
+namespace sicp {
+
+static thread_local std::string g_thread_error;
+void set_thread_error(const std::string& m) { g_thread_error = m; }
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+namespace {
+
+constexpr int kMaxRecords = 4096;
+
+__global__ void k_iota(long long* p, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+__global__ void k_check_sel(const long long* __restrict__ sel, long long K, long long n,
+                            unsigned int* __restrict__ bad) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const long long v = sel[i];
+  if (v < 0 || v >= n || (i > 0 && sel[i - 1] >= v)) atomicAdd(bad, 1u);
+}
+
+__global__ void k_range_keep(const double* __restrict__ d2, long long K, double r2,
+                             uint8_t* __restrict__ keep, unsigned int* __restrict__ count) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  unsigned int k = 0;
+  if (i < K) {
+    k = (d2[i] < r2) ? 1u : 0u;  // strict: cKDTree distance_upper_bound semantics
+    keep[i] = (uint8_t)k;
+  }
+  const unsigned int m = __ballot_sync(0xffffffffu, k);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned int)__popc(m));
+}
+
+__global__ void k_split_f4(const float4* __restrict__ in, long long K, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const float4 v = in[i];
+  out[i] = v.x;
+  out[K + i] = v.y;
+  out[2 * K + i] = v.z;
+  out[3 * K + i] = v.w;
+}
+
+__global__ void k_join_f4(const float* __restrict__ in, long long K, float4* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  out[i] = make_float4(in[i], in[K + i], in[2 * K + i], in[3 * K + i]);
+}
+
+void copy_any(Ctx& c, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return;
+  SICP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c.stream));
+}
+
+void sync(Ctx& c) { SICP_CUDA(cudaStreamSynchronize(c.stream)); }
+
+void init_state(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_loop) {
+  // small pageable H2D copies are staged by the runtime before the call returns
+  DevState h;
+  if (reset_loop) {
+    std::memset(&h, 0, sizeof(h));
+  } else {
+    SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    sync(c);
+  }
+  if (x)
+    for (int j = 0; j < 6; ++j) h.x[j] = x[j];
+  h.T = T_or_null ? *T_or_null : rigid_from_x(h.x);
+  h.Tinv = rigid_inverse(h.T);
+  if (reset_loop) h.stop = 0;
+  SICP_CUDA(cudaMemcpyAsync(c.dev_state.p, &h, sizeof(h), cudaMemcpyHostToDevice, c.stream));
+  sync(c);
+}
+
+void require_clouds(Ctx& c) {
+  SICP_REQUIRE(c.n_fix > 0 && c.n_mov > 0, SICP_ERR_STATE, "sicp_set_clouds has not been called");
+}
+void require_selected(Ctx& c) {
+  require_clouds(c);
+  SICP_REQUIRE(c.K > 0, SICP_ERR_STATE, "no fixed points are selected");
+}
+void require_normals(Ctx& c) {
+  require_selected(c);
+  SICP_REQUIRE(c.have_normals, SICP_ERR_STATE,
+               "normals are missing: call sicp_estimate_normals or sicp_set_normals first");
+}
+
+void fetch_records(Ctx& c, int first, int count) {
+  SICP_CUDA(cudaMemcpyAsync(c.rec_host + first, c.ws.rec.p + first, sizeof(sicp_iter_record) * count,
+                            cudaMemcpyDeviceToHost, c.stream));
+}
+
+}  // namespace
+
+void set_state_transform(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_loop) {
+  init_state(c, x, T_or_null, reset_loop);
+}
+
+}  // namespace sicp
+
+using namespace sicp;
+
+#define API_BEGIN(ctxptr)                                    \
+  if (!(ctxptr)) {                                           \
+    sicp::set_thread_error("sicp_ctx is NULL");              \
+    return SICP_ERR_BAD_ARG;                                 \
+  }                                                          \
+  Ctx& c = (ctxptr)->c;                                      \
+  try {                                                      \
+    SICP_CUDA(cudaSetDevice(c.device));
+
+#define API_END                                              \
+  }                                                          \
+  catch (const sicp::Error& e) {                             \
+    c.err = e.msg;                                           \
+    sicp::set_thread_error(e.msg);                           \
+    if (e.code == SICP_ERR_CUDA) cudaGetLastError();         \
+    return e.code;                                           \
+  }                                                          \
+  catch (const std::exception& e) {                          \
+    c.err = e.what();                                        \
+    sicp::set_thread_error(c.err);                           \
+    return SICP_ERR_CUDA;                                    \
+  }                                                          \
+  return SICP_OK;
+
+extern "C" {
+
+int32_t sicp_abi_version(void) { return SICP_ABI_VERSION; }
+
+const char* sicp_last_error(sicp_ctx* ctx) {
+  if (ctx) return ctx->c.err.c_str();
+  return sicp::g_thread_error.c_str();
+}
+
+int32_t sicp_create(int32_t device, void* cuda_stream, sicp_ctx** out) {
+  if (!out) {
+    sicp::set_thread_error("out is NULL");
+    return SICP_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    sicp::set_thread_error(std::string("no CUDA device available: ") + cudaGetErrorString(e));
+    return SICP_ERR_CUDA;
+  }
+  if (device < 0 || device >= n_dev) {
+    sicp::set_thread_error("device index out of range");
+    return SICP_ERR_BAD_ARG;
+  }
+  sicp_ctx* h = new (std::nothrow) sicp_ctx();
+  if (!h) return SICP_ERR_CUDA;
+  Ctx& c = h->c;
+  try {
+    c.device = device;
+    SICP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SICP_CUDA(cudaGetDeviceProperties(&prop, device));
+    SICP_REQUIRE(prop.major >= 10, SICP_ERR_CUDA,
+                 std::string("libsicp_b200 is built for sm_100a only; device is sm_") +
+                     std::to_string(prop.major) + std::to_string(prop.minor));
+    c.num_sms = prop.multiProcessorCount;
+    c.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    SICP_CUDA(cudaEventCreate(&c.ev0));
+    SICP_CUDA(cudaEventCreate(&c.ev1));
+    SICP_CUDA(cudaMallocHost(&c.rec_host, sizeof(sicp_iter_record) * kMaxRecords));
+    SICP_CUDA(cudaMallocHost(&c.scal_host, sizeof(double) * 256));
+    c.ws.rec.reserve(kMaxRecords);
+    c.ws.scal.reserve(256);
+    c.ws.counters.reserve(64);
+    c.ws.minkey.reserve(16);
+    c.dev_state.reserve(1);
+    SICP_CUDA(cudaMemsetAsync(c.dev_state.p, 0, sizeof(DevState), c.stream));
+    SICP_CUDA(cudaStreamSynchronize(c.stream));
+  } catch (const sicp::Error& er) {
+    sicp::set_thread_error(er.msg);
+    delete h;
+    return er.code;
+  }
+  *out = h;
+  return SICP_OK;
+}
+
+int32_t sicp_destroy(sicp_ctx* ctx) {
+  if (!ctx) return SICP_OK;
+  Ctx& c = ctx->c;
+  cudaSetDevice(c.device);
+  cudaStreamSynchronize(c.stream);
+  if (c.ev0) cudaEventDestroy(c.ev0);
+  if (c.ev1) cudaEventDestroy(c.ev1);
+  if (c.rec_host) cudaFreeHost(c.rec_host);
+  if (c.scal_host) cudaFreeHost(c.scal_host);
+  delete ctx;
+  return SICP_OK;
+}
+
+int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(key != nullptr, SICP_ERR_BAD_ARG, "key is NULL");
+  const std::string k(key);
+  if (k == "nn_engine") {
+    SICP_REQUIRE(value == 0 || value == 1 || value == 2, SICP_ERR_BAD_ARG, "nn_engine must be 0, 1 or 2");
+    c.nn_engine = (int)value;
+  } else if (k == "sign_mode") {
+    SICP_REQUIRE(value == 0 || value == 1, SICP_ERR_BAD_ARG, "sign_mode must be 0 or 1");
+    c.sign_mode = (int)value;
+  } else if (k == "grid_target_occupancy") {
+    SICP_REQUIRE(value >= 0.25 && value <= 64, SICP_ERR_BAD_ARG, "grid_target_occupancy out of range");
+    c.grid_target_occ = value;
+  } else if (k == "grid_max_rings") {
+    SICP_REQUIRE(value >= 1 && value <= 1e6, SICP_ERR_BAD_ARG, "grid_max_rings out of range");
+    c.grid_max_rings = (int)value;
+  } else if (k == "host_sync_every") {
+    SICP_REQUIRE(value >= 1 && value <= 1024, SICP_ERR_BAD_ARG, "host_sync_every out of range");
+    c.host_sync_every = (int)value;
+  } else {
+    SICP_REQUIRE(false, SICP_ERR_BAD_ARG, "unknown option: " + k);
+  }
+  API_END
+}
+
+int32_t sicp_set_selected(sicp_ctx* ctx, const int64_t* idx, int64_t K) {
+  API_BEGIN(ctx)
+  require_clouds(c);
+  SICP_REQUIRE(K > 0 && K <= c.n_fix, SICP_ERR_BAD_ARG, "K must be in [1, n_fix]");
+  c.sel_idx.reserve(K);
+  if (idx == nullptr) {
+    SICP_REQUIRE(K == c.n_fix, SICP_ERR_BAD_ARG, "idx == NULL selects all points: K must equal n_fix");
+    k_iota<<<(unsigned)((K + 255) / 256), 256, 0, c.stream>>>(c.sel_idx.p, K);
+  } else {
+    copy_any(c, c.sel_idx.p, idx, sizeof(long long) * K);
+    SICP_CUDA(cudaMemsetAsync(c.misc_counters.p + 8, 0, sizeof(unsigned int), c.stream));
+    k_check_sel<<<(unsigned)((K + 255) / 256), 256, 0, c.stream>>>(c.sel_idx.p, K, c.n_fix,
+                                                                  c.misc_counters.p + 8);
+    unsigned int bad = 0;
+    SICP_CUDA(cudaMemcpyAsync(&bad, c.misc_counters.p + 8, sizeof(bad), cudaMemcpyDeviceToHost, c.stream));
+    sync(c);
+    SICP_REQUIRE(bad == 0, SICP_ERR_BAD_ARG,
+                 "selected indices must be strictly ascending and inside [0, n_fix)");
+  }
+  c.K = K;
+  gather_queries_launch(c);
+  c.have_normals = false;
+  c.matched = c.rejected = c.solved = false;
+  sync(c);
+  API_END
+}
+
+int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, const double* mov_xyz,
+                        int64_t n_mov) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(fix_xyz && mov_xyz, SICP_ERR_BAD_ARG, "cloud pointer is NULL");
+  SICP_REQUIRE(n_fix > 0 && n_mov > 0, SICP_ERR_BAD_ARG, "clouds must not be empty");
+  SICP_REQUIRE(n_fix < (1ll << 31) && n_mov < (1ll << 31), SICP_ERR_BAD_ARG,
+               "clouds are limited to 2^31 - 1 points");
+  {
+    StageTimer t(c, &c.tm.upload_ms);
+    c.fix_xyz.reserve(3 * n_fix);
+    c.mov_xyz.reserve(3 * n_mov);
+    copy_any(c, c.fix_xyz.p, fix_xyz, sizeof(double) * 3 * n_fix);
+    copy_any(c, c.mov_xyz.p, mov_xyz, sizeof(double) * 3 * n_mov);
+    t.stop();
+  }
+  c.n_fix = n_fix;
+  c.n_mov = n_mov;
+  c.gfix.built = false;
+  {
+    StageTimer t(c, &c.tm.grid_mov_ms);
+    grid_build(c, c.gmov, c.mov_xyz.p, n_mov);
+    make_float4_copy(c);
+    t.stop();
+  }
+  c.K = 0;
+  c.have_normals = false;
+  c.matched = c.rejected = c.solved = false;
+  API_END
+}
+
+int32_t sicp_select_in_range(sicp_ctx* ctx, const double H0[16], double max_range, uint8_t* keep,
+                             int64_t* n_kept) {
+  API_BEGIN(ctx)
+  require_selected(c);
+  SICP_REQUIRE(H0 && n_kept, SICP_ERR_BAD_ARG, "NULL argument");
+  SICP_REQUIRE(max_range > 0, SICP_ERR_BAD_ARG, "max_range must be > 0");
+  const Rigid T = rigid_from_H(H0);
+  init_state(c, nullptr, &T, true);
+  StageTimer t(c, &c.tm.overlap_ms);
+  c.dist.reserve(c.K);
+  c.keep.reserve(c.K);
+  // the overlap filter needs no normals: the epilogue is skipped (with_distance = false)
+  match_launch(c, false, c.dist.p);
+  SICP_CUDA(cudaMemsetAsync(c.misc_counters.p + 8, 0, sizeof(unsigned int), c.stream));
+  k_range_keep<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(
+      c.dist.p, c.K, max_range * max_range, c.keep.p, c.misc_counters.p + 8);
+  unsigned int cnt = 0;
+  SICP_CUDA(cudaMemcpyAsync(&cnt, c.misc_counters.p + 8, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
+  if (keep) copy_any(c, keep, c.keep.p, (size_t)c.K);
+  t.stop();
+  *n_kept = cnt;
+  SICP_REQUIRE(cnt > 0, SICP_ERR_NO_OVERLAP,
+               "Point clouds do not overlap within max_overlap_distance");
+  API_END
+}
+
+int32_t sicp_estimate_normals(sicp_ctx* ctx, int32_t neighbors, float* nx, float* ny, float* nz,
+                              float* planarity) {
+  API_BEGIN(ctx)
+  require_selected(c);
+  if (!c.gfix.built) {
+    StageTimer t(c, &c.tm.grid_fix_ms);
+    grid_build(c, c.gfix, c.fix_xyz.p, c.n_fix);
+    t.stop();
+  }
+  StageTimer t(c, &c.tm.normals_ms);
+  estimate_normals_launch(c, neighbors);
+  c.have_normals = true;
+  if (nx || ny || nz || planarity) {
+    c.stage.reserve(sizeof(float) * 4 * c.K);
+    float* s = reinterpret_cast<float*>(c.stage.p);
+    k_split_f4<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(c.q_nrm.p, c.K, s);
+    if (nx) copy_any(c, nx, s, sizeof(float) * c.K);
+    if (ny) copy_any(c, ny, s + c.K, sizeof(float) * c.K);
+    if (nz) copy_any(c, nz, s + 2 * c.K, sizeof(float) * c.K);
+    if (planarity) copy_any(c, planarity, s + 3 * c.K, sizeof(float) * c.K);
+  }
+  t.stop();
+  API_END
+}
+
+int32_t sicp_set_normals(sicp_ctx* ctx, const float* nx, const float* ny, const float* nz,
+                         const float* planarity) {
+  API_BEGIN(ctx)
+  require_selected(c);
+  SICP_REQUIRE(nx && ny && nz && planarity, SICP_ERR_BAD_ARG, "NULL normal array");
+  c.stage.reserve(sizeof(float) * 4 * c.K);
+  float* s = reinterpret_cast<float*>(c.stage.p);
+  copy_any(c, s, nx, sizeof(float) * c.K);
+  copy_any(c, s + c.K, ny, sizeof(float) * c.K);
+  copy_any(c, s + 2 * c.K, nz, sizeof(float) * c.K);
+  copy_any(c, s + 3 * c.K, planarity, sizeof(float) * c.K);
+  c.q_nrm.reserve(c.K);
+  k_join_f4<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(s, c.K, c.q_nrm.p);
+  c.have_normals = true;
+  sync(c);
+  API_END
+}
+
+int32_t sicp_get_knn(sicp_ctx* ctx, int64_t* idx, double* dist2) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(c.knn_k > 0 && c.have_normals, SICP_ERR_STATE, "sicp_estimate_normals has not run");
+  if (idx) copy_any(c, idx, c.knn_idx.p, sizeof(long long) * c.K * c.knn_k);
+  if (dist2) copy_any(c, dist2, c.knn_d2.p, sizeof(double) * c.K * c.knn_k);
+  sync(c);
+  API_END
+}
+
+int32_t sicp_match(sicp_ctx* ctx, const double H[16], int64_t* pc2_idx, double* dist) {
+  API_BEGIN(ctx)
+  require_normals(c);
+  SICP_REQUIRE(H != nullptr, SICP_ERR_BAD_ARG, "H is NULL");
+  const Rigid T = rigid_from_H(H);
+  init_state(c, nullptr, &T, true);
+  StageTimer t(c, &c.tm.match_ms);
+  match_launch(c, true, nullptr);
+  if (pc2_idx) copy_any(c, pc2_idx, c.nn_idx.p, sizeof(long long) * c.K);
+  if (dist) copy_any(c, dist, c.dist.p, sizeof(double) * c.K);
+  t.stop();
+  c.matched = true;
+  c.rejected = c.solved = false;
+  API_END
+}
+
+int32_t sicp_reject(sicp_ctx* ctx, double min_planarity, uint8_t* keep, int64_t* n_kept,
+                    double stats[4]) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(c.matched, SICP_ERR_STATE, "sicp_match has not been called");
+  SICP_REQUIRE(n_kept != nullptr, SICP_ERR_BAD_ARG, "n_kept is NULL");
+  sicp_run_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.min_planarity = min_planarity;
+  p.lsq.distance_weight = 1.0;
+  reject_solve_launch(c, p, 0, false, false, 0);
+  fetch_records(c, 0, 1);
+  if (keep) copy_any(c, keep, c.keep.p, (size_t)c.K);
+  sync(c);
+  const sicp_iter_record& r = c.rec_host[0];
+  *n_kept = r.n_kept;
+  c.n_kept = r.n_kept;
+  if (stats) {
+    stats[0] = r.median;
+    stats[1] = r.mad;
+    stats[2] = r.mean_dist;
+    stats[3] = r.std_dist;
+  }
+  c.min_planarity_last = min_planarity;
+  c.rejected = true;
+  API_END
+}
+
+int32_t sicp_solve(sicp_ctx* ctx, const sicp_lsq_params* lp, double x[6], double H[16],
+                   double* residuals, double stats[2], double* distance_weight_used) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(c.rejected, SICP_ERR_STATE, "sicp_reject has not been called");
+  SICP_REQUIRE(lp && x && H, SICP_ERR_BAD_ARG, "NULL argument");
+  sicp_run_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.min_planarity = c.min_planarity_last;
+  p.min_change = 0.0;
+  p.lsq = *lp;
+  // keep the matching transform (it only fixes the centring), start the solve from x0
+  DevState h;
+  SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  sync(c);
+  for (int j = 0; j < 6; ++j) h.x[j] = lp->x0[j];
+  h.stop = 0;
+  h.w = 0.0;
+  SICP_CUDA(cudaMemcpyAsync(c.dev_state.p, &h, sizeof(h), cudaMemcpyHostToDevice, c.stream));
+  StageTimer t(c, &c.tm.reject_solve_ms);
+  reject_solve_launch(c, p, 0, true, false, 0);
+  t.stop();
+  fetch_records(c, 0, 1);
+  SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  sync(c);
+  const sicp_iter_record& r = c.rec_host[0];
+  c.n_kept = r.n_kept;
+  SICP_REQUIRE(r.n_kept >= 6, SICP_ERR_TOO_FEW_CORR,
+               "Too few correspondences! At least 6 correspondences are needed to estimate the 6 "
+               "rigid body transformation parameters. The current number of correspondences is " +
+                   std::to_string(r.n_kept) + ".");
+  SICP_REQUIRE(h.lm_ok, SICP_ERR_SINGULAR, "normal equations are singular");
+  for (int j = 0; j < 6; ++j) {
+    x[j] = r.x[j];
+    c.last_x[j] = r.x[j];
+    c.last_sigma[j] = h.sigma[j];
+  }
+  H_from_rigid(h.T, H);
+  if (stats) {
+    stats[0] = r.mean_res;
+    stats[1] = r.std_res;
+  }
+  if (distance_weight_used) *distance_weight_used = r.distance_weight;
+  if (residuals) {
+    compact_residuals_launch(c);
+    copy_any(c, residuals, c.resid_compact.p, sizeof(double) * r.n_kept);
+    sync(c);
+  }
+  c.solved = true;
+  API_END
+}
+
+int32_t sicp_uncertainties(sicp_ctx* ctx, double sigma[6]) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(c.solved, SICP_ERR_STATE, "no solve has been run");
+  SICP_REQUIRE(sigma != nullptr, SICP_ERR_BAD_ARG, "sigma is NULL");
+  for (int j = 0; j < 6; ++j) sigma[j] = c.last_sigma[j];
+  API_END
+}
+
+int32_t sicp_iterate(sicp_ctx* ctx, const sicp_run_params* p, const double x_in[6],
+                     sicp_iter_record* rec) {
+  API_BEGIN(ctx)
+  require_normals(c);
+  SICP_REQUIRE(p != nullptr, SICP_ERR_BAD_ARG, "params is NULL");
+  if (x_in) {
+    init_state(c, x_in, nullptr, true);
+    ctx->it_counter = 0;
+  }
+  match_launch(c, true, nullptr);
+  reject_solve_launch(c, *p, ctx->it_counter, true, false, 0);
+  ctx->it_counter++;
+  c.matched = c.rejected = true;
+  if (rec) {
+    fetch_records(c, 0, 1);
+    sync(c);
+    *rec = c.rec_host[0];
+  }
+  API_END
+}
+
+int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
+                 sicp_iter_record* log) {
+  API_BEGIN(ctx)
+  require_normals(c);
+  SICP_REQUIRE(p && out, SICP_ERR_BAD_ARG, "NULL argument");
+  SICP_REQUIRE(p->max_iterations >= 1 && p->max_iterations <= kMaxRecords, SICP_ERR_BAD_ARG,
+               "max_iterations must be in [1, 4096]");
+  bool any_finite = false;
+  for (int j = 0; j < 6; ++j) {
+    SICP_REQUIRE(p->lsq.obs_weight[j] >= 0, SICP_ERR_BAD_ARG,
+                 "All elements of rbp_observation_weights must be >= 0.");
+    any_finite = any_finite || std::isfinite(p->lsq.obs_weight[j]);
+  }
+  SICP_REQUIRE(any_finite, SICP_ERR_BAD_ARG,
+               "At least one element in rbp_observation_weights must be finite.");
+  init_state(c, p->lsq.x0, nullptr, true);
+  std::memset(out, 0, sizeof(*out));
+
+  cudaEvent_t e0, e1;
+  SICP_CUDA(cudaEventCreate(&e0));
+  SICP_CUDA(cudaEventCreate(&e1));
+  SICP_CUDA(cudaEventRecord(e0, c.stream));
+  int done = 0, fetched = 0, converged = 0;
+  DevState h;
+  const int every = std::max(1, c.host_sync_every);
+  for (int it = 0; it < p->max_iterations; ++it) {
+    match_launch(c, true, nullptr);
+    reject_solve_launch(c, *p, it, true, true, it);
+    if ((it + 1) % every == 0 || it + 1 == p->max_iterations) {
+      fetch_records(c, fetched, it + 1 - fetched);
+      SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+      sync(c);
+      fetched = it + 1;
+      done = h.iterations_done;
+      if (h.stop == 2 || (done < it + 1 && !h.stop)) {
+        // an iteration ended with fewer than 6 correspondences
+        const long long nk = c.rec_host[std::min(done, it)].n_kept;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        SICP_REQUIRE(false, SICP_ERR_TOO_FEW_CORR,
+                     "Too few correspondences! At least 6 correspondences are needed to estimate "
+                     "the 6 rigid body transformation parameters. The current number of "
+                     "correspondences is " + std::to_string(nk) + ".");
+      }
+      if (h.stop == 1) {
+        converged = 1;
+        break;
+      }
+    }
+  }
+  SICP_CUDA(cudaEventRecord(e1, c.stream));
+  compact_residuals_launch(c);
+  SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  sync(c);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  done = h.iterations_done;
+  SICP_REQUIRE(h.lm_ok, SICP_ERR_SINGULAR, "normal equations are singular");
+  out->iterations = done;
+  out->converged = converged;
+  for (int j = 0; j < 6; ++j) {
+    out->x[j] = h.x[j];
+    out->sigma[j] = h.sigma[j];
+    c.last_x[j] = h.x[j];
+    c.last_sigma[j] = h.sigma[j];
+  }
+  H_from_rigid(h.T, out->H);
+  out->n_residuals = h.n_kept;
+  out->loop_ms = ms;
+  c.n_kept = h.n_kept;
+  c.tm.match_ms = 0;
+  c.tm.reject_solve_ms = ms;
+  if (log) std::memcpy(log, c.rec_host, sizeof(sicp_iter_record) * done);
+  c.matched = c.rejected = c.solved = true;
+  API_END
+}
+
+int32_t sicp_get_residuals(sicp_ctx* ctx, double* residuals, int64_t cap, int64_t* n) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(c.solved, SICP_ERR_STATE, "no solve has been run");
+  SICP_REQUIRE(n != nullptr, SICP_ERR_BAD_ARG, "n is NULL");
+  *n = c.n_kept;
+  if (residuals) {
+    SICP_REQUIRE(cap >= c.n_kept, SICP_ERR_BAD_ARG, "residual buffer too small");
+    copy_any(c, residuals, c.resid_compact.p, sizeof(double) * c.n_kept);
+    sync(c);
+  }
+  API_END
+}
+
+int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out) {
+  API_BEGIN(ctx)
+  require_clouds(c);
+  SICP_REQUIRE(H && mov_xyz_out, SICP_ERR_BAD_ARG, "NULL argument");
+  const Rigid T = rigid_from_H(H);
+  StageTimer t(c, &c.tm.transform_ms);
+  if (is_device_ptr(mov_xyz_out)) {
+    transform_launch(c, T, c.mov_xyz.p, mov_xyz_out, c.n_mov);
+  } else {
+    c.stage.reserve(sizeof(double) * 3 * c.n_mov);
+    double* s = reinterpret_cast<double*>(c.stage.p);
+    transform_launch(c, T, c.mov_xyz.p, s, c.n_mov);
+    copy_any(c, mov_xyz_out, s, sizeof(double) * 3 * c.n_mov);
+  }
+  t.stop();
+  API_END
+}
+
+int32_t sicp_get_timings(sicp_ctx* ctx, sicp_timings* t) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(t != nullptr, SICP_ERR_BAD_ARG, "t is NULL");
+  *t = c.tm;
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// ctx.cuh — the context behind sicp_ctx and the stage entry points each .cu implements.
+#pragma once
+#include "common.cuh"
+#include "reject_solve.cuh"
+
+namespace sicp {
+
+// Cell-sorted copy of one cloud + its uniform grid (HBM resident, L2 resident for <= ~2M points).
+struct Grid {
+  DevBuf<Rec> recs;              // n points, sorted by cell
+  DevBuf<uint32_t> cell_start;   // n_cells + 1
+  DevBuf<uint32_t> cid;          // scratch: cell id per point
+  DevBuf<uint32_t> fill;         // scratch: per-cell counter
+  DevBuf<uint32_t> block_sums;   // scratch for the scan
+  double o[3] = {0, 0, 0};
+  double h = 1.0;
+  int dims[3] = {1, 1, 1};
+  long long n = 0;
+  long long n_cells = 0;
+  long long n_occupied = 0;
+  bool built = false;
+  GridView view() const {
+    GridView v;
+    v.recs = recs.p;
+    v.cell_start = cell_start.p;
+    v.ox = o[0];
+    v.oy = o[1];
+    v.oz = o[2];
+    v.h = h;
+    v.inv_h = 1.0 / h;
+    v.nx = dims[0];
+    v.ny = dims[1];
+    v.nz = dims[2];
+    v.n_points = n;
+    return v;
+  }
+};
+
+// Workspace of the fused reject + solve kernel (all device memory).
+struct SolveWs {
+  DevBuf<unsigned int> hist;        // radix histograms: 2 selects x levels x bins
+  DevBuf<unsigned long long> cand;  // candidate keys for the in-block sort, 2 selects
+  DevBuf<unsigned int> counters;    // small atomic counters / flags
+  DevBuf<unsigned long long> minkey;  // min key above the selected bin, per select
+  DevBuf<double> partials;          // per-block partial sums
+  DevBuf<double> scal;              // broadcast scalars: median, mad, x, ...
+  DevBuf<sicp_iter_record> rec;     // device copy of the per-iteration record ring
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  std::string err;
+
+  // options
+  int nn_engine = SICP_NN_AUTO;
+  int sign_mode = SICP_SIGN_CANONICAL;
+  double grid_target_occ = 3.0;
+  int grid_max_rings = 4;
+  int host_sync_every = 1;
+
+  // clouds
+  DevBuf<double> fix_xyz, mov_xyz;
+  long long n_fix = 0, n_mov = 0;
+  DevBuf<float4> mov_f4;  // centred float copy in caller order, for the TMA brute-force engine
+  double mov_center[3] = {0, 0, 0};
+  double mov_radius = 0;  // max |centred coordinate|
+  Grid gmov, gfix;
+
+  // selection (ascending fixed-cloud indices) and per-query data
+  long long K = 0;
+  DevBuf<long long> sel_idx;
+  DevBuf<double> q_xyz;   // K x 3 gathered fixed points
+  DevBuf<float4> q_nrm;   // (nx, ny, nz, planarity) float32 as the reference stores them
+  bool have_normals = false;
+  int knn_k = 0;
+  DevBuf<long long> knn_idx;
+  DevBuf<double> knn_d2;
+
+  // per-iteration arrays
+  DevBuf<long long> nn_idx;
+  DevBuf<double> dist;
+  DevBuf<uint8_t> keep;
+  DevBuf<double> resid;          // K, valid where keep
+  DevBuf<double> resid_compact;  // kept order
+  DevBuf<unsigned int> unresolved;  // query ids the grid could not bound + counter at [K]
+  DevBuf<unsigned char> bf_scratch;
+  long long n_kept = 0;
+  bool matched = false, rejected = false, solved = false;
+  double min_planarity_last = 0.0;
+
+  // last solve state (for uncertainties)
+  double last_x[6] = {0, 0, 0, 0, 0, 0};
+  double last_sigma[6] = {0, 0, 0, 0, 0, 0};
+  sicp_lsq_params last_lsq{};
+
+  SolveWs ws;
+  DevBuf<DevState> dev_state;
+  int rs_parity = 0;
+  DevBuf<unsigned int> compact_sums;
+  DevBuf<unsigned long long> bbox_keys;   // grid build scratch (kept apart from the select workspace)
+  DevBuf<unsigned int> misc_counters;     // grid build / API scratch counters
+  sicp_iter_record* rec_host = nullptr;  // pinned
+  double* scal_host = nullptr;           // pinned staging for small reads
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  sicp_timings tm{};
+
+  // staging for host inputs
+  DevBuf<unsigned char> stage;
+};
+
+// ---- stage entry points (each implemented in its own translation unit) ---------------------
+void grid_build(Ctx& c, Grid& g, const double* xyz_dev, long long n);
+void make_float4_copy(Ctx& c);
+
+// 1-NN of K transformed queries into the movable cloud; fused point-to-plane distance.
+// If out_d2 != nullptr the squared NN distance is written instead of the plane distance epilogue
+// being required (overlap filter).
+// The transform is read from c.dev_state (T, Tinv) on the device.
+void match_launch(Ctx& c, bool with_distance, double* out_d2);
+void set_state_transform(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_loop);
+void estimate_normals_launch(Ctx& c, int k);
+void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve, bool arm_stop,
+                         int rec_slot);
+void compact_residuals_launch(Ctx& c);
+void transform_launch(Ctx& c, const Rigid& T, const double* in_dev, double* out_dev, long long n);
+void gather_queries_launch(Ctx& c);
+
+// helpers in capi.cu
+bool is_device_ptr(const void* p);
+
+struct StageTimer {
+  Ctx& c;
+  double* slot;
+  StageTimer(Ctx& c_, double* s) : c(c_), slot(s) { cudaEventRecord(c.ev0, c.stream); }
+  void stop() {
+    cudaEventRecord(c.ev1, c.stream);
+    cudaEventSynchronize(c.ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+    *slot = ms;
+  }
+};
+
+}  // namespace sicp

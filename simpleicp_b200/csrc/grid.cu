@@ -1,0 +1,334 @@
+// grid.cu — build the static uniform grid over a cloud (done ONCE per cloud; the reference
+// rebuilds a kd-tree over the transformed movable cloud every iteration,
+// python/simpleicp/corrpts.py:131 — here the cloud never moves, the queries do).
+//
+// Pipeline (all HBM-streaming, one pass each over n points or n_cells cells):
+//   k_bbox        : min/max of x,y,z                (reads 24 n B)
+//   k_cell_count  : cell id per point + histogram   (reads 24 n B, n atomics into L2)
+//   scan          : exclusive prefix over cells     (reads/writes 4 n_cells B, 3 kernels)
+//   k_scatter     : cell-sorted 32-byte records     (reads 28 n B, writes 32 n B)
+#include <algorithm>
+
+#include "ctx.cuh"
+
+namespace sicp {
+
+namespace {
+
+constexpr int kScanItems = 4096;  // cells per scan block (256 threads x 16)
+
+__global__ void __launch_bounds__(256) k_bbox(const double* __restrict__ xyz, long long n,
+                                              unsigned long long* __restrict__ out) {
+  double mn[3] = {kInf, kInf, kInf}, mx[3] = {-kInf, -kInf, -kInf};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double v = xyz[3 * i + a];
+      mn[a] = fmin(mn[a], v);
+      mx[a] = fmax(mx[a], v);
+    }
+  }
+  __shared__ double smn[8][3], smx[8][3];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = warp_min(mn[a]);
+    mx[a] = warp_max(mx[a]);
+    if (lane == 0) {
+      smn[w][a] = mn[a];
+      smx[w][a] = mx[a];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int a = threadIdx.x;
+    double lo = smn[0][a], hi = smx[0][a];
+    for (int i = 1; i < 8; ++i) {
+      lo = fmin(lo, smn[i][a]);
+      hi = fmax(hi, smx[i][a]);
+    }
+    atomicMin(&out[a], f64_to_key(lo));
+    atomicMax(&out[3 + a], f64_to_key(hi));
+  }
+}
+
+__global__ void k_bbox_init(unsigned long long* out) {
+  if (threadIdx.x < 3) out[threadIdx.x] = ~0ull;
+  else if (threadIdx.x < 6) out[threadIdx.x] = 0ull;
+}
+__global__ void k_bbox_decode(const unsigned long long* in, double* out) {
+  if (threadIdx.x < 6) out[threadIdx.x] = key_to_f64(in[threadIdx.x]);
+}
+
+struct GridParams {
+  double ox, oy, oz, inv_h;
+  int nx, ny, nz;
+};
+
+__global__ void __launch_bounds__(256) k_cell_count(const double* __restrict__ xyz, long long n,
+                                                    GridParams g, uint32_t* __restrict__ cid,
+                                                    uint32_t* __restrict__ count) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cx = cell_coord(xyz[3 * i + 0], g.ox, g.inv_h, g.nx);
+  int cy = cell_coord(xyz[3 * i + 1], g.oy, g.inv_h, g.ny);
+  int cz = cell_coord(xyz[3 * i + 2], g.oz, g.inv_h, g.nz);
+  uint32_t c = (uint32_t)(((long long)cz * g.ny + cy) * g.nx + cx);
+  cid[i] = c;
+  atomicAdd(&count[c], 1u);
+}
+
+// ---- 3-kernel exclusive scan over uint32 (n up to 2^27) ------------------------------------
+__global__ void __launch_bounds__(256) k_scan_reduce(const uint32_t* __restrict__ in, long long n,
+                                                     uint32_t* __restrict__ block_sums,
+                                                     unsigned int* __restrict__ n_nonzero) {
+  long long base = (long long)blockIdx.x * kScanItems;
+  uint32_t s = 0, nz = 0;
+  for (int j = threadIdx.x; j < kScanItems; j += 256) {
+    long long i = base + j;
+    if (i < n) {
+      uint32_t v = in[i];
+      s += v;
+      nz += (v != 0);
+    }
+  }
+  __shared__ uint32_t sh[8], shz[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    nz += __shfl_xor_sync(0xffffffffu, nz, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = s;
+    shz[threadIdx.x >> 5] = nz;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0, tz = 0;
+    for (int i = 0; i < 8; ++i) {
+      t += sh[i];
+      tz += shz[i];
+    }
+    block_sums[blockIdx.x] = t;
+    if (tz) atomicAdd(n_nonzero, tz);
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocksums(uint32_t* __restrict__ block_sums, int nb) {
+  // single block, sequential chunks of 1024 with a running carry
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = (i < nb) ? block_sums[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      uint32_t t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    uint32_t incl = sh[threadIdx.x];
+    uint32_t c = carry;
+    if (i < nb) block_sums[i] = c + incl - v;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + incl;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scan_down(const uint32_t* __restrict__ in, long long n,
+                                                   const uint32_t* __restrict__ block_offsets,
+                                                   uint32_t* __restrict__ out) {
+  // each thread owns 16 consecutive items
+  long long base = (long long)blockIdx.x * kScanItems + threadIdx.x * 16;
+  uint32_t v[16];
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    long long i = base + j;
+    v[j] = (i < n) ? in[i] : 0;
+    s += v[j];
+  }
+  // block-wide exclusive scan of s
+  __shared__ uint32_t wsum[8];
+  uint32_t incl = s;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int i = 0; i < w; ++i) woff += wsum[i];
+  uint32_t run = block_offsets[blockIdx.x] + woff + incl - s;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    long long i = base + j;
+    if (i < n) out[i] = run;
+    run += v[j];
+  }
+}
+
+__global__ void k_scan_total(const uint32_t* __restrict__ in, long long n,
+                             uint32_t* __restrict__ out) {
+  // out[n] = out[n-1] + in[n-1]
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[n] = (n > 0) ? out[n - 1] + in[n - 1] : 0;
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const double* __restrict__ xyz, long long n,
+                                                 const uint32_t* __restrict__ cid,
+                                                 const uint32_t* __restrict__ cell_start,
+                                                 uint32_t* __restrict__ fill,
+                                                 Rec* __restrict__ recs) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c = cid[i];
+  uint32_t pos = cell_start[c] + atomicAdd(&fill[c], 1u);
+  Rec r;
+  r.x = xyz[3 * i + 0];
+  r.y = xyz[3 * i + 1];
+  r.z = xyz[3 * i + 2];
+  r.idx = i;
+  recs[pos] = r;
+}
+
+// Cells hold their points in arrival order of the atomics; sort each cell by original index so
+// the layout (and therefore every memory trace) is reproducible run to run.  Cells are tiny
+// (target occupancy ~3), insertion sort by one thread per cell.
+__global__ void __launch_bounds__(256) k_sort_cells(const uint32_t* __restrict__ cell_start,
+                                                    long long n_cells, Rec* __restrict__ recs) {
+  long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  uint32_t s = cell_start[c], e = cell_start[c + 1];
+  for (uint32_t i = s + 1; i < e; ++i) {
+    Rec r = recs[i];
+    uint32_t j = i;
+    while (j > s && recs[j - 1].idx > r.idx) {
+      recs[j] = recs[j - 1];
+      --j;
+    }
+    recs[j] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_float4_copy(const double* __restrict__ xyz, long long n,
+                                                     long long n_pad, double cx, double cy,
+                                                     double cz, float4* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  float4 v;
+  if (i < n) {
+    v.x = (float)(xyz[3 * i + 0] - cx);
+    v.y = (float)(xyz[3 * i + 1] - cy);
+    v.z = (float)(xyz[3 * i + 2] - cz);
+    v.w = 0.f;
+  } else {
+    v.x = v.y = v.z = 3.0e18f;  // padding: never the nearest neighbour
+    v.w = 0.f;
+  }
+  out[i] = v;
+}
+
+}  // namespace
+
+void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
+  cudaStream_t st = c.stream;
+  g.built = false;
+  g.n = n;
+  // ---- bounding box
+  c.bbox_keys.reserve(16);
+  c.ws.scal.reserve(256);
+  k_bbox_init<<<1, 32, 0, st>>>(c.bbox_keys.p);
+  int nb = (int)std::min<long long>((n + 255) / 256, (long long)c.num_sms * 8);
+  k_bbox<<<std::max(nb, 1), 256, 0, st>>>(xyz, n, c.bbox_keys.p);
+  k_bbox_decode<<<1, 32, 0, st>>>(c.bbox_keys.p, c.ws.scal.p);
+  SICP_CUDA(cudaMemcpyAsync(c.scal_host, c.ws.scal.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaStreamSynchronize(st));
+  double lo[3], ext[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = c.scal_host[a];
+    ext[a] = c.scal_host[3 + a] - c.scal_host[a];
+    SICP_REQUIRE(isfinite(lo[a]) && isfinite(ext[a]), SICP_ERR_BAD_ARG,
+                 "point cloud contains non-finite coordinates");
+  }
+  // ---- initial cell size: assume a 2-D manifold in 3-D (scans): h ~ sqrt(target * A / n) with A
+  // the product of the two largest extents; refined below from the measured occupancy.
+  double e[3] = {ext[0], ext[1], ext[2]};
+  std::sort(e, e + 3);
+  double emax = std::max(e[2], 1e-12);
+  double area = std::max(e[2] * std::max(e[1], 1e-3 * emax), 1e-300);
+  double h = sqrt(c.grid_target_occ * area / (double)std::max<long long>(n, 1));
+  h = std::max(h, emax * 1e-6);
+  const long long kMaxCells = 1ll << 25;  // 32 M cells (128 MB of cell_start)
+  c.misc_counters.reserve(64);
+
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    long long d[3];
+    for (;;) {
+      for (int a = 0; a < 3; ++a) d[a] = std::max<long long>(1, (long long)floor(ext[a] / h) + 1);
+      if (d[0] * d[1] * d[2] <= kMaxCells) break;
+      h *= 1.26;  // 2x fewer cells per step
+    }
+    g.h = h;
+    for (int a = 0; a < 3; ++a) {
+      g.o[a] = lo[a];
+      g.dims[a] = (int)d[a];
+    }
+    g.n_cells = d[0] * d[1] * d[2];
+    g.cell_start.reserve(g.n_cells + 1);
+    g.fill.reserve(g.n_cells);
+    g.cid.reserve(n);
+    long long nsb = (g.n_cells + kScanItems - 1) / kScanItems;
+    g.block_sums.reserve(nsb + 1);
+    SICP_CUDA(cudaMemsetAsync(g.fill.p, 0, g.n_cells * sizeof(uint32_t), st));
+    SICP_CUDA(cudaMemsetAsync(c.misc_counters.p, 0, 64 * sizeof(unsigned int), st));
+    GridParams gp{g.o[0], g.o[1], g.o[2], 1.0 / h, g.dims[0], g.dims[1], g.dims[2]};
+    k_cell_count<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, n, gp, g.cid.p, g.fill.p);
+    k_scan_reduce<<<(unsigned)nsb, 256, 0, st>>>(g.fill.p, g.n_cells, g.block_sums.p, c.misc_counters.p);
+    k_scan_blocksums<<<1, 1024, 0, st>>>(g.block_sums.p, (int)nsb);
+    k_scan_down<<<(unsigned)nsb, 256, 0, st>>>(g.fill.p, g.n_cells, g.block_sums.p, g.cell_start.p);
+    k_scan_total<<<1, 32, 0, st>>>(g.fill.p, g.n_cells, g.cell_start.p);
+    unsigned int nocc = 0;
+    SICP_CUDA(cudaMemcpyAsync(&nocc, c.misc_counters.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    g.n_occupied = nocc;
+    double occ = (double)n / (double)std::max<unsigned int>(nocc, 1u);
+    // accept when within a factor 1.6 of the target, or when the cell cap binds
+    if (attempt == 3 || (occ <= c.grid_target_occ * 1.6 && occ >= c.grid_target_occ / 1.6)) break;
+    if (occ > c.grid_target_occ && d[0] * d[1] * d[2] * 2 > kMaxCells) break;  // cannot refine
+    // occupancy of occupied cells scales ~ h^dim with dim in [2,3] for scan data; use 2.3
+    double f = pow(c.grid_target_occ / occ, 1.0 / 2.3);
+    f = std::min(std::max(f, 0.25), 4.0);
+    h *= f;
+  }
+  g.recs.reserve(n);
+  SICP_CUDA(cudaMemsetAsync(g.fill.p, 0, g.n_cells * sizeof(uint32_t), st));
+  k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, n, g.cid.p, g.cell_start.p, g.fill.p,
+                                                        g.recs.p);
+  k_sort_cells<<<(unsigned)((g.n_cells + 255) / 256), 256, 0, st>>>(g.cell_start.p, g.n_cells,
+                                                                   g.recs.p);
+  SICP_CUDA(cudaGetLastError());
+  g.built = true;
+}
+
+void make_float4_copy(Ctx& c) {
+  // centred float4 copy of the movable cloud in caller order (TMA brute-force engine)
+  const GridView v = c.gmov.view();
+  double hi[3] = {v.ox + v.nx * v.h, v.oy + v.ny * v.h, v.oz + v.nz * v.h};
+  c.mov_center[0] = 0.5 * (v.ox + hi[0]);
+  c.mov_center[1] = 0.5 * (v.oy + hi[1]);
+  c.mov_center[2] = 0.5 * (v.oz + hi[2]);
+  c.mov_radius = 0.5 * std::max(hi[0] - v.ox, std::max(hi[1] - v.oy, hi[2] - v.oz));
+  long long n_pad = ((c.n_mov + kBfTile - 1) / kBfTile) * kBfTile;
+  c.mov_f4.reserve(n_pad);
+  k_float4_copy<<<(unsigned)((n_pad + 255) / 256), 256, 0, c.stream>>>(
+      c.mov_xyz.p, c.n_mov, n_pad, c.mov_center[0], c.mov_center[1], c.mov_center[2], c.mov_f4.p);
+  SICP_CUDA(cudaGetLastError());
+}
+
+}  // namespace sicp

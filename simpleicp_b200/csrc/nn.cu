@@ -1,0 +1,444 @@
+// nn.cu — nearest-neighbour correspondence search (reference: CorrPts.match,
+// python/simpleicp/corrpts.py:124-137 + 195-211, and PointCloud.select_in_range,
+// python/simpleicp/pointcloud.py:149-171).
+//
+// The reference transforms the whole movable cloud by H, rebuilds a kd-tree and queries it with
+// the selected fixed points.  Rigid maps preserve distances, so here the K queries are moved by
+// H^-1 instead and searched in a STATIC structure over the original movable cloud; only the
+// matched point is moved by H for the point-to-plane distance.
+//
+// Two exact engines:
+//   grid  : uniform-grid search in float64, 3x3x3 block then shell-by-shell ring expansion until
+//           the best distance is provably <= the distance to every unexplored cell.
+//   brute : tiled exhaustive search.  float4 tiles of the (centred, float32) cloud are staged
+//           into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, 4-stage ring),
+//           lanes split the tile, float32 distances act as a FILTER with a rigorous error margin,
+//           every candidate that passes is re-evaluated in float64 from the original
+//           coordinates, and the per-lane winners are combined with a warp-shuffle min-reduction.
+// Ties are broken towards the lower original index in both.
+#include <algorithm>
+
+#include "ctx.cuh"
+
+namespace sicp {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// grid engine
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scan_range(const Rec* __restrict__ recs, uint32_t s, uint32_t e,
+                                           double qx, double qy, double qz, double& best,
+                                           long long& bidx) {
+  for (uint32_t i = s; i < e; ++i) {
+    const Rec r = recs[i];  // one LDG.E.256
+    const double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 < best || (d2 == best && r.idx < bidx)) {
+      best = d2;
+      bidx = r.idx;
+    }
+  }
+}
+
+// Returns true when (best, bidx) is proven to be the nearest neighbour.
+__device__ bool grid_nn(const GridView& g, double qx, double qy, double qz, int rmax, double& best,
+                        long long& bidx) {
+  const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+  best = kInf;
+  bidx = -1;
+  const uint32_t* __restrict__ cs = g.cell_start;
+  for (int r = 1;; ++r) {
+    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
+    const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
+    const int za = max(z0, 0), zb = min(z1, g.nz - 1);
+    const int ya = max(y0, 0), yb = min(y1, g.ny - 1);
+    for (int z = za; z <= zb; ++z) {
+      for (int y = ya; y <= yb; ++y) {
+        const long long row = ((long long)z * g.ny + y) * g.nx;
+        const bool full = (r == 1) || z == z0 || z == z1 || y == y0 || y == y1;
+        if (full) {
+          scan_range(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, best, bidx);
+        } else {
+          if (x0 >= 0) scan_range(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, best, bidx);
+          if (x1 < g.nx) scan_range(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, best, bidx);
+        }
+      }
+    }
+    // distance from the query to the nearest face behind which unexplored cells remain
+    double guard = kInf;
+    if (x0 > 0) guard = fmin(guard, qx - (g.ox + x0 * g.h));
+    if (x1 < g.nx - 1) guard = fmin(guard, (g.ox + (x1 + 1) * g.h) - qx);
+    if (y0 > 0) guard = fmin(guard, qy - (g.oy + y0 * g.h));
+    if (y1 < g.ny - 1) guard = fmin(guard, (g.oy + (y1 + 1) * g.h) - qy);
+    if (z0 > 0) guard = fmin(guard, qz - (g.oz + z0 * g.h));
+    if (z1 < g.nz - 1) guard = fmin(guard, (g.oz + (z1 + 1) * g.h) - qz);
+    if (guard >= kInf) return true;  // the block covers the whole grid
+    guard -= 1e-9 * g.h;             // cell assignment of points rounds at the 1e-13 level
+    if (guard > 0.0 && best <= guard * guard) return true;
+    if (r >= rmax) return false;
+  }
+}
+
+// signed point-to-plane distance exactly as the reference evaluates it (corrpts.py:198-209):
+// (dx*nx + dy*ny) + dz*nz with the float32 normal promoted to float64, no fused multiply-add.
+__device__ __forceinline__ double plane_distance(const Rigid& T, const double* __restrict__ mov_xyz,
+                                                 long long j, double px, double py, double pz,
+                                                 float4 nrm) {
+  double tx, ty, tz;
+  rigid_apply(T, mov_xyz[3 * j + 0], mov_xyz[3 * j + 1], mov_xyz[3 * j + 2], tx, ty, tz);
+  const double dx = tx - px, dy = ty - py, dz = tz - pz;
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, (double)nrm.x), __dmul_rn(dy, (double)nrm.y)),
+                   __dmul_rn(dz, (double)nrm.z));
+}
+
+__global__ void __launch_bounds__(128)
+    k_match_grid(GridView g, const DevState* __restrict__ st, const double* __restrict__ q_xyz,
+                 const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz, long long K,
+                 int rmax, int with_distance, long long* __restrict__ nn_idx,
+                 double* __restrict__ out, unsigned int* __restrict__ unresolved) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= K || st->stop) return;
+  const Rigid Tinv = st->Tinv;
+  const double px = q_xyz[3 * i + 0], py = q_xyz[3 * i + 1], pz = q_xyz[3 * i + 2];
+  double qx, qy, qz;
+  rigid_apply(Tinv, px, py, pz, qx, qy, qz);
+  double best;
+  long long bidx;
+  const bool ok = grid_nn(g, qx, qy, qz, rmax, best, bidx);
+  if (!ok) {
+    const unsigned int slot = atomicAdd(&unresolved[K], 1u);
+    unresolved[slot] = (unsigned int)i;
+    return;
+  }
+  nn_idx[i] = bidx;
+  out[i] = with_distance ? plane_distance(st->T, mov_xyz, bidx, px, py, pz, q_nrm[i]) : best;
+}
+
+// ------------------------------------------------------------------------------------------
+// brute-force engine (TMA staged)
+// ------------------------------------------------------------------------------------------
+constexpr int BF_TILE = kBfTile;  // float4 points per stage = 32 KB
+constexpr int BF_STAGES = 4;    // 128 KB of shared memory in flight
+constexpr int BF_THREADS = 256; // 8 warps
+constexpr int BF_QPW = 8;       // queries per warp
+constexpr int BF_QPB = BF_QPW * (BF_THREADS / 32);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct BfPartial {
+  double d2;
+  long long idx;
+};
+
+// float32 filter margin: |d32 - d_true| <= e(d) for every point, with eta the per-coordinate
+// rounding error of the centred float32 coordinates (see DESIGN.md "brute-force exactness").
+__device__ __forceinline__ float bf_threshold(float best32, double eta) {
+  const double d = (double)best32;
+  const double e = 4.0 * eta * sqrt(d) + 1.0e-6 * d + 4.0 * eta * eta;
+  const double t = d + 2.5 * e;
+  float f = (float)t;
+  if ((double)f < t) f = nextafterf(f, 3.0e38f);
+  return f;
+}
+
+__global__ void __launch_bounds__(BF_THREADS, 1)
+    k_bf_nn(const float4* __restrict__ mov_f4, const double* __restrict__ mov_xyz, long long n_mov,
+            long long n_pad, double cx, double cy, double cz, double radius,
+            const DevState* __restrict__ st,
+            const double* __restrict__ q_xyz, const unsigned int* __restrict__ qlist,
+            const unsigned int* __restrict__ qcount_ptr, long long q_total, int tiles_per_chunk,
+            BfPartial* __restrict__ partials) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* tiles = reinterpret_cast<float4*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)BF_STAGES * BF_TILE * sizeof(float4));
+  uint64_t* empty = full + BF_STAGES;
+  double* q64 = reinterpret_cast<double*>(empty + BF_STAGES);  // BF_QPB x 3
+
+  const long long nq = qlist ? (long long)(*qcount_ptr) : q_total;
+  const long long n_groups = (nq + BF_QPB - 1) / BF_QPB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_tiles = n_pad / BF_TILE;
+  const long long tile0 = (long long)blockIdx.y * tiles_per_chunk;
+  const long long tile1 = min(tile0 + tiles_per_chunk, n_tiles);
+  if (tile0 >= tile1 || n_groups == 0 || st->stop) return;
+  const int my_tiles = (int)(tile1 - tile0);
+  const Rigid Tinv = st->Tinv;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < BF_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], BF_THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t it_base = 0;  // tiles consumed so far by this block (across query groups)
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    // ---- queries of this warp: move into the movable frame, centre, round to float32
+    float ax[BF_QPW], ay[BF_QPW], az[BF_QPW], best32[BF_QPW], thr[BF_QPW];
+    double best64[BF_QPW], eta[BF_QPW];
+    long long bidx[BF_QPW];
+#pragma unroll
+    for (int k = 0; k < BF_QPW; ++k) {
+      const long long qi = grp * BF_QPB + warp * BF_QPW + k;
+      double mx = 0, my = 0, mz = 0;
+      if (qi < nq) {
+        const long long q = qlist ? (long long)qlist[qi] : qi;
+        rigid_apply(Tinv, q_xyz[3 * q + 0], q_xyz[3 * q + 1], q_xyz[3 * q + 2], mx, my, mz);
+      }
+      if (lane == 0) {
+        q64[(warp * BF_QPW + k) * 3 + 0] = mx;
+        q64[(warp * BF_QPW + k) * 3 + 1] = my;
+        q64[(warp * BF_QPW + k) * 3 + 2] = mz;
+      }
+      const double a0 = mx - cx, a1 = my - cy, a2 = mz - cz;
+      ax[k] = (float)a0;
+      ay[k] = (float)a1;
+      az[k] = (float)a2;
+      eta[k] = 1.1920929e-7 * (fmax(fabs(a0), fmax(fabs(a1), fabs(a2))) + radius) * 1.5;
+      best32[k] = 3.0e38f;
+      thr[k] = 3.0e38f;
+      best64[k] = kInf;
+      bidx[k] = -1;
+    }
+    __syncwarp();
+
+    // ---- producer prologue: fill the ring
+    if (threadIdx.x == 0) {
+      for (int t = 0; t < min(BF_STAGES, my_tiles); ++t) {
+        const uint32_t g_it = it_base + t;
+        const int s = g_it % BF_STAGES;
+        if (g_it >= BF_STAGES) mbar_wait(&empty[s], ((g_it / BF_STAGES) - 1) & 1);
+        mbar_expect_tx(&full[s], BF_TILE * sizeof(float4));
+        tma_load_1d(tiles + (size_t)s * BF_TILE, mov_f4 + (tile0 + t) * BF_TILE,
+                    BF_TILE * sizeof(float4), &full[s]);
+      }
+    }
+
+    for (int t = 0; t < my_tiles; ++t) {
+      const uint32_t g_it = it_base + t;
+      const int s = g_it % BF_STAGES;
+      mbar_wait(&full[s], (g_it / BF_STAGES) & 1);
+      const float4* __restrict__ tp = tiles + (size_t)s * BF_TILE;
+      const long long base = (tile0 + t) * BF_TILE;
+#pragma unroll 2
+      for (int j = lane; j < BF_TILE; j += 32) {
+        const float4 p = tp[j];  // conflict-free LDS.128
+#pragma unroll
+        for (int k = 0; k < BF_QPW; ++k) {
+          const float dx = p.x - ax[k], dy = p.y - ay[k], dz = p.z - az[k];
+          const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          if (d <= thr[k]) {
+            // rare: exact float64 re-evaluation from the original coordinates
+            const long long gi = base + j;
+            if (gi < n_mov) {
+              const double* qq = &q64[(warp * BF_QPW + k) * 3];
+              const double ex = mov_xyz[3 * gi + 0] - qq[0];
+              const double ey = mov_xyz[3 * gi + 1] - qq[1];
+              const double ez = mov_xyz[3 * gi + 2] - qq[2];
+              const double d64 = ex * ex + ey * ey + ez * ez;
+              if (d64 < best64[k] || (d64 == best64[k] && gi < bidx[k])) {
+                best64[k] = d64;
+                bidx[k] = gi;
+              }
+              if (d < best32[k]) {
+                best32[k] = d;
+                thr[k] = bf_threshold(d, eta[k]);
+              }
+            }
+          }
+        }
+      }
+      // share the float32 bound across the warp so every lane filters with the tightest one
+#pragma unroll
+      for (int k = 0; k < BF_QPW; ++k) {
+        float m = best32[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m < best32[k]) {
+          best32[k] = m;
+          thr[k] = bf_threshold(m, eta[k]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      // producer: refill this stage with tile t + BF_STAGES once every warp has released it
+      if (threadIdx.x == 0 && t + BF_STAGES < my_tiles) {
+        mbar_wait(&empty[s], (g_it / BF_STAGES) & 1);
+        mbar_expect_tx(&full[s], BF_TILE * sizeof(float4));
+        tma_load_1d(tiles + (size_t)s * BF_TILE, mov_f4 + (tile0 + t + BF_STAGES) * BF_TILE,
+                    BF_TILE * sizeof(float4), &full[s]);
+      }
+    }
+    it_base += my_tiles;
+
+    // ---- warp-shuffle lexicographic min-reduction of (d64, idx) over the lanes
+#pragma unroll
+    for (int k = 0; k < BF_QPW; ++k) {
+      double d = best64[k];
+      long long ix = bidx[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (od < d || (od == d && oi >= 0 && (ix < 0 || oi < ix))) {
+          d = od;
+          ix = oi;
+        }
+      }
+      const long long qi = grp * BF_QPB + warp * BF_QPW + k;
+      if (lane == 0 && qi < nq) {
+        BfPartial pr;
+        pr.d2 = d;
+        pr.idx = ix;
+        partials[(long long)blockIdx.y * q_total + qi] = pr;
+      }
+    }
+    __syncthreads();  // q64 is reused by the next group
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    k_bf_finalize(const BfPartial* __restrict__ partials, int n_chunks, long long q_total,
+                  const unsigned int* __restrict__ qlist, const unsigned int* __restrict__ qcount_ptr,
+                  const DevState* __restrict__ st, const double* __restrict__ q_xyz,
+                  const float4* __restrict__ q_nrm,
+                  const double* __restrict__ mov_xyz, int with_distance,
+                  long long* __restrict__ nn_idx, double* __restrict__ out) {
+  const long long nq = qlist ? (long long)(*qcount_ptr) : q_total;
+  const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (qi >= nq || st->stop) return;
+  const Rigid T = st->T;
+  double d = kInf;
+  long long ix = -1;
+  for (int c = 0; c < n_chunks; ++c) {
+    const BfPartial p = partials[(long long)c * q_total + qi];
+    if (p.idx >= 0 && (p.d2 < d || (p.d2 == d && p.idx < ix) || ix < 0)) {
+      d = p.d2;
+      ix = p.idx;
+    }
+  }
+  const long long q = qlist ? (long long)qlist[qi] : qi;
+  nn_idx[q] = ix;
+  out[q] = with_distance ? plane_distance(T, mov_xyz, ix, q_xyz[3 * q + 0], q_xyz[3 * q + 1],
+                                          q_xyz[3 * q + 2], q_nrm[q])
+                         : d;
+}
+
+__global__ void __launch_bounds__(256)
+    k_gather_queries(const double* __restrict__ fix_xyz, const long long* __restrict__ sel,
+                     long long K, double* __restrict__ q_xyz) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const long long j = sel[i];
+  q_xyz[3 * i + 0] = fix_xyz[3 * j + 0];
+  q_xyz[3 * i + 1] = fix_xyz[3 * j + 1];
+  q_xyz[3 * i + 2] = fix_xyz[3 * j + 2];
+}
+
+constexpr size_t kBfSmem =
+    (size_t)BF_STAGES * BF_TILE * sizeof(float4) + 2 * BF_STAGES * sizeof(uint64_t) +
+    (size_t)BF_QPB * 3 * sizeof(double);
+
+}  // namespace
+
+void gather_queries_launch(Ctx& c) {
+  c.q_xyz.reserve(3 * std::max<long long>(c.K, 1));
+  k_gather_queries<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(c.fix_xyz.p, c.sel_idx.p,
+                                                                       c.K, c.q_xyz.p);
+  SICP_CUDA(cudaGetLastError());
+}
+
+// Brute-force pass over either the unresolved list (qlist != nullptr) or all K queries.
+static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SICP_CUDA(cudaFuncSetAttribute(k_bf_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBfSmem));
+    attr_set = true;
+  }
+  const long long n_tiles = (c.n_mov + BF_TILE - 1) / BF_TILE;
+  SICP_REQUIRE(c.mov_f4.cap >= (size_t)n_tiles * BF_TILE, SICP_ERR_STATE,
+               "float4 copy not padded to the brute-force tile");
+  const long long q_total = c.K;
+  // grid: x = query groups (grid-stride), y = point chunks
+  long long groups_hint = whole_set ? (c.K + BF_QPB - 1) / BF_QPB : 4;
+  int gx = (int)std::min<long long>(std::max<long long>(groups_hint, 1), 4096);
+  long long want_blocks = 2ll * c.num_sms;
+  int n_chunks = (int)std::min<long long>(std::max<long long>(want_blocks / gx, 1), n_tiles);
+  int tiles_per_chunk = (int)((n_tiles + n_chunks - 1) / n_chunks);
+  n_chunks = (int)((n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+  c.bf_scratch.reserve((size_t)n_chunks * q_total * sizeof(BfPartial));
+  BfPartial* partials = reinterpret_cast<BfPartial*>(c.bf_scratch.p);
+  const unsigned int* qlist = whole_set ? nullptr : c.unresolved.p;
+  const unsigned int* qcount = whole_set ? nullptr : c.unresolved.p + c.K;
+  dim3 grid(gx, n_chunks);
+  k_bf_nn<<<grid, BF_THREADS, kBfSmem, c.stream>>>(
+      c.mov_f4.p, c.mov_xyz.p, c.n_mov, n_tiles * BF_TILE, c.mov_center[0], c.mov_center[1],
+      c.mov_center[2], c.mov_radius, c.dev_state.p, c.q_xyz.p, qlist, qcount, q_total,
+      tiles_per_chunk,
+      partials);
+  k_bf_finalize<<<(unsigned)((q_total + 127) / 128), 128, 0, c.stream>>>(
+      partials, n_chunks, q_total, qlist, qcount, c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p,
+      with_distance ? 1 : 0, c.nn_idx.p, out);
+  SICP_CUDA(cudaGetLastError());
+}
+
+void match_launch(Ctx& c, bool with_distance, double* out_d2) {
+  const long long K = c.K;
+  c.nn_idx.reserve(K);
+  c.dist.reserve(K);
+  c.unresolved.reserve(K + 1);
+  double* out = with_distance ? c.dist.p : out_d2;
+  if (c.nn_engine == SICP_NN_BRUTE) {
+    bf_launch(c, with_distance, out, true);
+    return;
+  }
+  SICP_CUDA(cudaMemsetAsync(c.unresolved.p + K, 0, sizeof(unsigned int), c.stream));
+  const int rmax = (c.nn_engine == SICP_NN_GRID) ? (1 << 30) : c.grid_max_rings;
+  k_match_grid<<<(unsigned)((K + 127) / 128), 128, 0, c.stream>>>(
+      c.gmov.view(), c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p, K, rmax, with_distance ? 1 : 0,
+      c.nn_idx.p, out, c.unresolved.p);
+  SICP_CUDA(cudaGetLastError());
+  if (c.nn_engine == SICP_NN_AUTO) bf_launch(c, with_distance, out, false);
+}
+
+}  // namespace sicp

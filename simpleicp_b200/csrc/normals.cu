@@ -1,0 +1,165 @@
+// normals.cu — PointCloud.estimate_normals (python/simpleicp/pointcloud.py:173-203):
+// k nearest neighbours (query point included) of every selected fixed point in the fixed cloud,
+// covariance with ddof = 1 (np.cov), symmetric 3x3 eigen-decomposition, normal = eigenvector of
+// the smallest eigenvalue, planarity = (l_mid - l_min) / l_max, both rounded to float32 exactly
+// where the reference does (pointcloud.py:180-183, 194-198).
+//
+// Fused: grid k-NN (float64, sorted top-k, exact ring expansion) -> covariance -> eigen-solve
+// -> float4 (nx, ny, nz, planarity) store; the neighbour lists never leave the SM unless the
+// caller asks for them.
+#include <algorithm>
+
+#include "ctx.cuh"
+#include "eig3.cuh"
+
+namespace sicp {
+
+namespace {
+
+constexpr int kMaxK = 64;
+
+struct TopK {
+  double d2[kMaxK];
+  long long idx[kMaxK];
+  int n;
+  int k;
+  __device__ __forceinline__ bool full() const { return n == k; }
+  __device__ __forceinline__ double worst() const { return d2[n - 1]; }
+  __device__ __forceinline__ void consider(double d, long long i) {
+    if (n == k) {
+      if (!(d < d2[k - 1] || (d == d2[k - 1] && i < idx[k - 1]))) return;
+    } else {
+      ++n;
+    }
+    int j = n - 1;
+    while (j > 0 && (d2[j - 1] > d || (d2[j - 1] == d && idx[j - 1] > i))) {
+      d2[j] = d2[j - 1];
+      idx[j] = idx[j - 1];
+      --j;
+    }
+    d2[j] = d;
+    idx[j] = i;
+  }
+};
+
+__device__ __forceinline__ void scan_range_k(const Rec* __restrict__ recs, uint32_t s, uint32_t e,
+                                             double qx, double qy, double qz, TopK& tk) {
+  for (uint32_t i = s; i < e; ++i) {
+    const Rec r = recs[i];
+    const double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
+    tk.consider(dx * dx + dy * dy + dz * dz, r.idx);
+  }
+}
+
+__device__ void grid_knn(const GridView& g, double qx, double qy, double qz, TopK& tk) {
+  const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+  const uint32_t* __restrict__ cs = g.cell_start;
+  for (int r = 1;; ++r) {
+    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
+    const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
+    const int za = max(z0, 0), zb = min(z1, g.nz - 1);
+    const int ya = max(y0, 0), yb = min(y1, g.ny - 1);
+    for (int z = za; z <= zb; ++z) {
+      for (int y = ya; y <= yb; ++y) {
+        const long long row = ((long long)z * g.ny + y) * g.nx;
+        const bool full = (r == 1) || z == z0 || z == z1 || y == y0 || y == y1;
+        if (full) {
+          scan_range_k(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, tk);
+        } else {
+          if (x0 >= 0) scan_range_k(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, tk);
+          if (x1 < g.nx) scan_range_k(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, tk);
+        }
+      }
+    }
+    double guard = kInf;
+    if (x0 > 0) guard = fmin(guard, qx - (g.ox + x0 * g.h));
+    if (x1 < g.nx - 1) guard = fmin(guard, (g.ox + (x1 + 1) * g.h) - qx);
+    if (y0 > 0) guard = fmin(guard, qy - (g.oy + y0 * g.h));
+    if (y1 < g.ny - 1) guard = fmin(guard, (g.oy + (y1 + 1) * g.h) - qy);
+    if (z0 > 0) guard = fmin(guard, qz - (g.oz + z0 * g.h));
+    if (z1 < g.nz - 1) guard = fmin(guard, (g.oz + (z1 + 1) * g.h) - qz);
+    if (guard >= kInf) return;
+    guard -= 1e-9 * g.h;
+    if (tk.full() && guard > 0.0 && tk.worst() <= guard * guard) return;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    k_knn_pca(GridView g, const double* __restrict__ fix_xyz, const double* __restrict__ q_xyz,
+              long long K, int k, int sign_mode, float4* __restrict__ q_nrm,
+              long long* __restrict__ knn_idx, double* __restrict__ knn_d2) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const double qx = q_xyz[3 * i + 0], qy = q_xyz[3 * i + 1], qz = q_xyz[3 * i + 2];
+  TopK tk;
+  tk.n = 0;
+  tk.k = k;
+  grid_knn(g, qx, qy, qz, tk);
+
+  // np.cov(pts.T, bias=False): subtract the mean, X X^T / (k - 1)
+  double mx = 0, my = 0, mz = 0;
+  for (int j = 0; j < tk.n; ++j) {
+    const long long p = tk.idx[j];
+    mx += fix_xyz[3 * p + 0];
+    my += fix_xyz[3 * p + 1];
+    mz += fix_xyz[3 * p + 2];
+    if (knn_idx) {
+      knn_idx[i * k + j] = p;
+      if (knn_d2) knn_d2[i * k + j] = tk.d2[j];
+    }
+  }
+  const double inv = 1.0 / (double)tk.n;
+  mx *= inv;
+  my *= inv;
+  mz *= inv;
+  double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+  for (int j = 0; j < tk.n; ++j) {
+    const long long p = tk.idx[j];
+    const double dx = fix_xyz[3 * p + 0] - mx, dy = fix_xyz[3 * p + 1] - my,
+                 dz = fix_xyz[3 * p + 2] - mz;
+    c00 = fma(dx, dx, c00);
+    c01 = fma(dx, dy, c01);
+    c02 = fma(dx, dz, c02);
+    c11 = fma(dy, dy, c11);
+    c12 = fma(dy, dz, c12);
+    c22 = fma(dz, dz, c22);
+  }
+  const double f = 1.0 / (double)(tk.n - 1);  // np.cov multiplies by true_divide(1, fact)
+  c00 *= f;
+  c01 *= f;
+  c02 *= f;
+  c11 *= f;
+  c12 *= f;
+  c22 *= f;
+
+  double w[3], n[3];
+  eig3_smallest(c00, c01, c02, c11, c12, c22, sign_mode, w, n);
+  // w sorted descending: planarity = (w1 - w2) / w0 (pointcloud.py:198), float32 store
+  float4 o;
+  o.x = (float)n[0];
+  o.y = (float)n[1];
+  o.z = (float)n[2];
+  o.w = (float)((w[1] - w[2]) / w[0]);
+  q_nrm[i] = o;
+}
+
+}  // namespace
+
+void estimate_normals_launch(Ctx& c, int k) {
+  SICP_REQUIRE(k >= 2 && k <= kMaxK, SICP_ERR_BAD_ARG,
+               "neighbors must be between 2 and 64 (got " + std::to_string(k) + ")");
+  SICP_REQUIRE((long long)k <= c.n_fix, SICP_ERR_BAD_ARG,
+               "neighbors exceeds the number of points in the fixed cloud");
+  c.q_nrm.reserve(std::max<long long>(c.K, 1));
+  c.knn_idx.reserve((size_t)c.K * k);
+  c.knn_d2.reserve((size_t)c.K * k);
+  c.knn_k = k;
+  k_knn_pca<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(
+      c.gfix.view(), c.fix_xyz.p, c.q_xyz.p, c.K, k, c.sign_mode, c.q_nrm.p, c.knn_idx.p,
+      c.knn_d2.p);
+  SICP_CUDA(cudaGetLastError());
+}
+
+}  // namespace sicp

@@ -1,0 +1,396 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors
+captured from the unmodified reference.  Tolerances are written next to each comparison:
+bit-exact for indices and masks, 1e-12 for float64 quantities computed the same way, and the
+reference solver's own slack (lmfit/TRF ftol = xtol = 1e-8 -> ~3e-6 per iteration, SURVEY.md
+§0.2) where the comparison crosses the least-squares solve."""
+import numpy as np
+import pytest
+from scipy.optimize import least_squares
+from scipy.spatial import cKDTree
+
+from conftest import load_golden, load_pair
+from oracle import simpleicp_oracle as O
+
+import simpleicp_b200 as sb
+from simpleicp_b200 import _capi
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = ["dragon", "bunny", "multisensor", "webots", "dragon_observed"]
+
+
+def obs_rad(kwargs):
+    obs = np.array(kwargs.get("rbp_observed_values", (0.0,) * 6), dtype=float)
+    obs[:3] *= np.pi / 180
+    return obs
+
+
+def H_inputs(g):
+    """H used for matching in every iteration of the golden run."""
+    xs = [obs_rad(g["kwargs"])] + [g["it_x"][i] for i in range(g["it_x"].shape[0] - 1)]
+    return [O.rbp_to_H(x) for x in xs]
+
+
+def full_normals(g, n_fix):
+    out = [np.full(n_fix, np.nan, dtype=np.float32) for _ in range(4)]
+    for a in range(3):
+        out[a][g["idx_sel"]] = g["normals"][:, a]
+    out[3][g["idx_sel"]] = g["planarity"]
+    return tuple(out)
+
+
+@pytest.fixture(scope="module")
+def engines(gpu):
+    cache = {}
+
+    def get(name, engine_mode=_capi.NN_AUTO):
+        key = (name, engine_mode)
+        if key not in cache:
+            g = load_golden(name)
+            X_fix, X_mov = load_pair(name)
+            e = _capi.Engine()
+            e.set_option("nn_engine", engine_mode)
+            e.set_clouds(X_fix, X_mov)
+            e.set_selected(g["idx_sel"])
+            e.set_normals(g["normals"][:, 0], g["normals"][:, 1], g["normals"][:, 2], g["planarity"])
+            cache[key] = (e, g, X_fix, X_mov)
+        return cache[key]
+
+    yield get
+    for e, *_ in cache.values():
+        e.close()
+
+
+def assert_same_nn(idx_gpu, idx_ref, q, X_mov_t, what):
+    """Indices equal; where they differ both candidates must be at the same distance (ties:
+    cKDTree's tie order is unspecified, ours is lowest index)."""
+    bad = np.flatnonzero(idx_gpu != idx_ref)
+    for i in bad:
+        da = np.linalg.norm(X_mov_t[idx_gpu[i]] - q[i])
+        db = np.linalg.norm(X_mov_t[idx_ref[i]] - q[i])
+        assert abs(da - db) <= 1e-12 * max(1.0, db), f"{what}: query {i}: {da} vs {db}"
+    return len(bad)
+
+
+@pytest.mark.parametrize("mode", [_capi.NN_AUTO, _capi.NN_GRID, _capi.NN_BRUTE])
+@pytest.mark.parametrize("name", CONFIGS)
+def test_match_lockstep(engines, name, mode):
+    """CorrPts.match for every golden iteration: pc2_idx identical, distances to 1e-12."""
+    e, g, X_fix, X_mov = engines(name, mode)
+    q = X_fix[g["idx_sel"]]
+    n_ties = 0
+    for it, H in enumerate(H_inputs(g)):
+        idx, d = e.match(H)
+        X_t = O.transform_by_H(X_mov, H)
+        n_ties += assert_same_nn(idx, g["it_pc2_idx"][it], q, X_t, f"{name} it {it}")
+        same = idx == g["it_pc2_idx"][it]
+        np.testing.assert_allclose(d[same], g["it_dist"][it][same], rtol=0, atol=1e-12)
+    assert n_ties <= 0.01 * q.shape[0] * len(H_inputs(g))
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_reject_lockstep(engines, name):
+    """Planarity + median/MAD rejection: keep mask bit-identical, median/MAD to 1e-15."""
+    e, g, X_fix, X_mov = engines(name)
+    for it, H in enumerate(H_inputs(g)):
+        idx, d = e.match(H)
+        keep, n_kept, st = e.reject(g["kwargs"].get("min_planarity", 0.3))
+        keep_o, med_o, mad_o = O.reject(d, g["planarity"], g["kwargs"].get("min_planarity", 0.3))
+        assert np.array_equal(keep, keep_o), f"{name} it {it}"
+        assert n_kept == int(keep_o.sum())
+        assert st[0] == med_o and st[1] == mad_o  # exact order statistics
+        if np.array_equal(idx, g["it_pc2_idx"][it]):
+            assert np.array_equal(keep, g["it_keep"][it])
+        np.testing.assert_allclose(st[2], d[keep].mean(), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(st[3], d[keep].std(), rtol=1e-10)
+
+
+def tight_solution(p1, n1, p2, w, x0, obs, w_obs):
+    obs, w_obs = np.asarray(obs, float), np.asarray(w_obs, float)
+    free = np.flatnonzero(np.isfinite(w_obs))
+    xf = np.array(x0, dtype=float)
+
+    def fun(v):
+        xf[free] = v
+        return O._residual_vector(xf, p1, n1.astype(np.float64), p2, w, obs, w_obs)
+
+    r = least_squares(fun, xf[free].copy(), xtol=1e-15, ftol=1e-15, gtol=1e-15, x_scale=1.0)
+    xf[free] = r.x
+    return xf.copy()
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_solve_lockstep(engines, name):
+    """estimate_parameters: x against a tightly converged SciPy solve of the same problem
+    (<= 1e-9), against the reference's lmfit result (its own ftol slack, <= 1e-5), residuals
+    at the solution against the oracle's residual function (<= 1e-12)."""
+    e, g, X_fix, X_mov = engines(name)
+    kw = g["kwargs"]
+    obs = obs_rad(kw)
+    w_obs = np.array(kw.get("rbp_observation_weights", (0.0,) * 6), dtype=float)
+    w = kw.get("distance_weights", 1)
+    x_prev = obs
+    for it, H in enumerate(H_inputs(g)):
+        idx, d = e.match(H)
+        keep, n_kept, st = e.reject(kw.get("min_planarity", 0.3))
+        w_it = g["it_w"][it] if w is None else w
+        x, Hs, res, rs, w_used = e.solve(x_prev, obs, w_obs, w_it, n_kept)
+        p1 = X_fix[g["idx_sel"][keep]]
+        p2 = X_mov[idx[keep]]
+        n1 = g["normals"][keep]
+        x_t = tight_solution(p1, n1, p2, w_it, x_prev, obs, w_obs)
+        np.testing.assert_allclose(x, x_t, rtol=0, atol=1e-9, err_msg=f"{name} it {it}")
+        if np.array_equal(keep, g["it_keep"][it]):
+            np.testing.assert_allclose(x, g["it_x"][it], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(Hs, O.rbp_to_H(x), rtol=0, atol=1e-15)
+        r_o = O._residual_vector(x, p1, n1.astype(np.float64), p2, 1.0, obs, np.zeros(6))
+        np.testing.assert_allclose(res, r_o, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(rs[0], res.mean(), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(rs[1], res.std(), rtol=1e-9)
+        # fixed parameters stay put
+        for j in range(6):
+            if not np.isfinite(w_obs[j]):
+                assert x[j] == x_prev[j]
+        sig = e.uncertainties()
+        # oracle sigmas from a finite-difference Jacobian at the GPU's solution
+        xo, res_u, res_w, jac = O.estimate_parameters(p1, n1, p2, w_it, x, obs, w_obs)
+        sig_o = O.estimate_parameter_uncertainties(res_w, jac, n_kept, w_it, w_obs)
+        np.testing.assert_allclose(sig, sig_o, rtol=1e-5, equal_nan=True)
+        x_prev = g["it_x"][it]
+
+
+def test_auto_distance_weight(engines):
+    """distance_weights=None: w = 1 / std(kept distances)^2 on iteration 0 (simpleicp.py:233)."""
+    e, g, X_fix, X_mov = engines("dragon_observed")
+    kw = g["kwargs"]
+    H = H_inputs(g)[0]
+    idx, d = e.match(H)
+    keep, n_kept, st = e.reject(0.3)
+    x, Hs, res, rs, w_used = e.solve(obs_rad(kw), obs_rad(kw), kw["rbp_observation_weights"], None, n_kept)
+    np.testing.assert_allclose(w_used, 1 / np.std(d[keep]) ** 2, rtol=1e-10)
+    np.testing.assert_allclose(w_used, g["it_w"][0], rtol=1e-10)
+
+
+@pytest.mark.parametrize("name,k", [("dragon", 10), ("bunny", 10), ("webots", 40), ("multisensor", 10)])
+def test_normals(gpu, name, k):
+    """k-NN + PCA: neighbour distances equal cKDTree's (1e-12), normals equal the reference's up
+    to sign (float32 store: 2e-7), planarity to 1e-6."""
+    g = load_golden(name)
+    X_fix, X_mov = load_pair(name)
+    with _capi.Engine() as e:
+        e.set_option("sign_mode", _capi.SIGN_CANONICAL)
+        e.set_clouds(X_fix, X_mov)
+        e.set_selected(g["idx_sel"])
+        nx, ny, nz, pl = e.estimate_normals(k)
+        idx_knn, d2 = e.get_knn(k)
+    dd, ii = cKDTree(X_fix).query(X_fix[g["idx_sel"]], k=k)
+    np.testing.assert_allclose(np.sqrt(d2), dd, rtol=0, atol=1e-12)
+    same_rows = (np.sort(idx_knn, axis=1) == np.sort(ii, axis=1)).all(axis=1)
+    assert same_rows.mean() > 0.98  # the rest are equal-distance ties at the k-th neighbour
+    n_gpu = np.column_stack((nx, ny, nz)).astype(np.float64)
+    n_ref = g["normals"].astype(np.float64)
+    ok = np.isfinite(g["planarity"]) & same_rows
+    dots = np.sum(n_gpu * n_ref, axis=1)
+    aligned = n_gpu * np.sign(dots)[:, None]
+    # poorly conditioned normals (nearly isotropic neighbourhoods) are excluded by the eigen gap
+    gap_ok = ok & (g["planarity"] > 0.05)
+    assert np.abs(aligned - n_ref)[gap_ok].max() < 5e-6
+    assert np.abs(aligned - n_ref)[gap_ok & (g["planarity"] > 0.3)].max() < 1e-6
+    np.testing.assert_allclose(pl[ok], g["planarity"][ok], rtol=0, atol=1e-6)
+    # canonical sign: largest-magnitude component positive
+    lead = np.take_along_axis(n_gpu, np.abs(n_gpu).argmax(axis=1)[:, None], axis=1)[:, 0]
+    assert (lead[np.isfinite(lead)] >= 0).all()
+
+
+@pytest.mark.parametrize("name", ["bunny", "multisensor", "webots"])
+def test_overlap_filter(gpu, name):
+    """select_in_range: the strictly-closer-than rule gives the reference's index set exactly."""
+    g = load_golden(name)
+    X_fix, X_mov = load_pair(name)
+    H0 = O.rbp_to_H(obs_rad(g["kwargs"]))
+    with _capi.Engine() as e:
+        e.set_clouds(X_fix, X_mov)
+        e.set_selected(None)
+        keep = e.select_in_range(H0, g["kwargs"]["max_overlap_distance"])
+    assert np.array_equal(np.flatnonzero(keep), g["idx_overlap"])
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_full_run_with_reference_normals(gpu, name):
+    """Whole pipeline with the reference's normals injected through the reference's own
+    pre-computed-columns hook: same iteration count, same kept counts, H within 1e-6 Frobenius
+    (expected ~1e-9: both sides sit on the same ICP fixed point)."""
+    g = load_golden(name)
+    X_fix, X_mov = load_pair(name)
+    res = sb.register(X_fix, X_mov, normals=full_normals(g, X_fix.shape[0]), **g["kwargs"])
+    assert np.array_equal(res.idx_selected, g["idx_sel"])
+    dH = np.linalg.norm(res.H - g["H"])
+    kept = [r["n_kept"] for r in res.records]
+    ref_kept = [int(k.sum()) for k in g["it_keep"]]
+    print(f"{name}: |dH|_F = {dH:.3e}, iterations {res.iterations} vs {len(ref_kept)}, kept {kept[-3:]} vs {ref_kept[-3:]}")
+    assert dH < 1e-6
+    assert res.iterations == len(ref_kept)
+    assert abs(kept[-1] - ref_kept[-1]) <= 2
+    if kept[-1] == ref_kept[-1]:
+        np.testing.assert_allclose(res.residuals, g["residuals"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(res.rbp.get_parameter_attributes_as_list("estimated_uncertainty"),
+                               g["sigma"], rtol=2e-2, equal_nan=True)
+    np.testing.assert_allclose(np.asarray(res.X_mov_transformed)[:64], g["X_mov_t_head"], rtol=0, atol=1e-5)
+
+
+def test_dragon_end_to_end_graded(gpu):
+    """BASELINE.json north star: H within 1e-5 Frobenius of the Python reference on data/dragon,
+    everything (normals included) computed on the GPU."""
+    g = load_golden("dragon")
+    X_fix, X_mov = load_pair("dragon")
+    H, X_t, rbp, res = sb.simpleicp(X_fix, X_mov)
+    dH = np.linalg.norm(H - g["H"])
+    print(f"dragon stand-alone |dH|_F = {dH:.3e}")
+    assert dH < 1e-5
+    np.testing.assert_allclose(np.asarray(X_t).sum(axis=0), g["X_mov_t_sum"], rtol=1e-6)
+
+
+def test_fused_loop_equals_stepwise(gpu):
+    g = load_golden("bunny")
+    X_fix, X_mov = load_pair("bunny")
+    nrm = full_normals(g, X_fix.shape[0])
+    a = sb.register(X_fix, X_mov, normals=nrm, **g["kwargs"])
+    b = sb.register(X_fix, X_mov, normals=nrm, stepwise=True, **g["kwargs"])
+    assert a.iterations == b.iterations
+    np.testing.assert_allclose(a.H, b.H, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(a.residuals, b.residuals, rtol=0, atol=1e-12)
+
+
+def test_host_sync_batching_is_equivalent(gpu):
+    """Queuing several iterations between host reads (device-side stop flag) changes nothing."""
+    g = load_golden("dragon")
+    X_fix, X_mov = load_pair("dragon")
+    nrm = full_normals(g, X_fix.shape[0])
+    a = sb.register(X_fix, X_mov, normals=nrm)
+    with _capi.Engine() as e:
+        e.set_option("host_sync_every", 4)
+        b = sb.register(X_fix, X_mov, normals=nrm, engine=e)
+    assert a.iterations == b.iterations
+    assert np.array_equal(a.H, b.H)
+
+
+def test_facade_side_effects(gpu):
+    """SimpleICP / PointCloud drop-in behaviour: pc_mov is transformed in place, pc_fix gains
+    float32 sparse normal columns and a thinned selection (reference: simpleicp.py:316,
+    pointcloud.py:200-203)."""
+    X_fix, X_mov = load_pair("bunny")
+    pc_fix = sb.PointCloud(X_fix, columns=["x", "y", "z"])
+    pc_mov = sb.PointCloud(X_mov, columns=["x", "y", "z"], copy=True)
+    icp = sb.SimpleICP(verbose=False)
+    icp.add_point_clouds(pc_fix, pc_mov)
+    H, X_t, rbp, res = icp.run(max_overlap_distance=1)
+    assert H.shape == (4, 4) and X_t.shape == X_mov.shape
+    np.testing.assert_allclose(X_t, O.transform_by_H(X_mov, H), rtol=0, atol=1e-12)
+    assert np.array_equal(pc_mov.X, X_t)
+    assert pc_fix.num_selected_points == 1000
+    assert str(pc_fix["planarity"].dtype) == "Sparse[float32, nan]"
+    assert np.isfinite(pc_fix["nx"].to_numpy()[pc_fix.idx_selected]).all()
+    assert isinstance(rbp, sb.RigidBodyParameters)
+    np.testing.assert_allclose(rbp.H, H, rtol=0, atol=1e-15)
+    assert len(res) > 6
+    g = load_golden("bunny")
+    assert np.linalg.norm(H - g["H"]) < 2e-3  # canonical normal sign: different kept sets
+    # second run reuses the stored normal columns (reference hook simpleicp.py:176-178)
+    pc_mov2 = sb.PointCloud(X_mov, columns=["x", "y", "z"], copy=True)
+    pc_fix.select_all_points()
+    icp.add_point_clouds(pc_fix, pc_mov2)
+    with pytest.raises(Exception):
+        # stored normals only cover the previously selected points: NaN planarity elsewhere
+        # drops every newly selected point -> fewer than 6 correspondences is possible but not
+        # guaranteed; accept either outcome, the call must not crash the process
+        icp.run(max_overlap_distance=1, min_planarity=2.0)
+
+
+def test_errors(gpu):
+    X_fix, X_mov = load_pair("bunny")
+    with pytest.raises(sb.SimpleICPException, match="do not overlap within max_overlap_distance = 0.50000"):
+        sb.simpleicp(X_fix, X_mov + 1000.0, max_overlap_distance=0.5)
+    with pytest.raises(sb.SimpleICPException, match="Too few correspondences"):
+        sb.simpleicp(X_fix, X_mov, min_planarity=2.0)
+    with pytest.raises(_capi.SicpError):
+        with _capi.Engine() as e:
+            e.match(np.eye(4))  # before set_clouds
+
+
+def test_transform(gpu):
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 1001, 100000):
+        X = rng.normal(size=(n, 3)) * 100
+        H = O.rbp_to_H([0.3, -0.2, 0.5, 10.0, -20.0, 30.0])
+        with _capi.Engine() as e:
+            e.set_clouds(X[:1], X)
+            Y = e.transform(H)
+            Z = np.empty_like(X)
+            np.testing.assert_allclose(Y, O.transform_by_H(X, H), rtol=0, atol=1e-12)
+            # round trip: transform of the transformed cloud by the inverse
+            e.set_clouds(X[:1], Y)
+            Z = e.transform(np.linalg.inv(H))
+        np.testing.assert_allclose(Z, X, rtol=0, atol=1e-11)
+
+
+def test_large_k_multi_block_path(gpu):
+    """K > 4096 switches the reject/solve kernel to its cooperative multi-block form; lock-step
+    against the oracle on dragon with 20 000 correspondences (normals from the oracle)."""
+    X_fix, X_mov = load_pair("dragon")
+    tr = O.Trace()
+    H_o, _, x_o, sig_o, res_o = O.simpleicp(X_fix, X_mov, correspondences=20000, trace=tr)
+    nrm = [np.full(X_fix.shape[0], np.nan, dtype=np.float32) for _ in range(4)]
+    for a in range(3):
+        nrm[a][tr.idx_sel] = tr.normals[:, a]
+    nrm[3][tr.idx_sel] = tr.planarity
+    with _capi.Engine() as e:
+        e.set_clouds(X_fix, X_mov)
+        e.set_selected(tr.idx_sel)
+        e.set_normals(tr.normals[:, 0], tr.normals[:, 1], tr.normals[:, 2], tr.planarity)
+        for it in tr.iterations:
+            idx, d = e.match(it.H_in)
+            keep, n_kept, st = e.reject(0.3)
+            keep_o, med_o, mad_o = O.reject(d, tr.planarity, 0.3)
+            assert np.array_equal(keep, keep_o)
+            assert st[0] == med_o and st[1] == mad_o
+            if np.array_equal(idx, it.pc2_idx):
+                assert np.array_equal(keep, it.keep)
+    res = sb.register(X_fix, X_mov, correspondences=20000, normals=tuple(nrm))
+    print(f"K=20000: |dH|_F = {np.linalg.norm(res.H - H_o):.3e}, it {res.iterations} vs {len(tr.iterations)}")
+    assert np.linalg.norm(res.H - H_o) < 1e-6
+    assert res.iterations == len(tr.iterations)
+
+
+def test_full_size_properties(gpu):
+    """BASELINE.json C3 size (1M <-> 1M, K = 100 000), size-independent properties:
+    recovers the known transform, grid and brute-force engines agree exactly, the converged
+    state is a fixed point, median/MAD equal NumPy's on the device distances."""
+    X_fix, X_mov, H_true = O.c3_pair(1_000_000)
+    with _capi.Engine() as e:
+        res = sb.register(X_fix, X_mov, correspondences=100_000, engine=e)
+        assert res.converged and res.iterations < 30
+        assert np.linalg.norm(res.H - H_true) < 2e-2
+        # the grid engine (all 100k queries) against the TMA brute-force engine on a sample
+        idx_g, d_g = e.match(res.H)
+        keep, n_kept, st = e.reject(0.3)
+        S1 = res.normals[3].astype(np.float64) >= 0.3
+        assert st[0] == np.median(d_g[S1])
+        assert st[1] == np.median(np.abs(d_g[S1] - st[0]))
+        assert np.array_equal(keep, S1 & (np.abs(d_g - st[0]) <= 3 * st[1]))
+    sample = res.idx_selected[:: 100_000 // 2048][:2048]
+    with _capi.Engine() as e2:
+        e2.set_option("nn_engine", _capi.NN_BRUTE)
+        e2.set_clouds(X_fix, X_mov)
+        e2.set_selected(sample)
+        pos = np.searchsorted(res.idx_selected, sample)
+        e2.set_normals(*[a[pos] for a in res.normals])
+        idx_b, d_b = e2.match(res.H)
+    assert np.array_equal(idx_b, idx_g[pos])
+    np.testing.assert_allclose(d_b, d_g[pos], rtol=0, atol=1e-13)
+    # fixed point: restarting from the solution changes nothing beyond the solver tolerance
+    x = np.array(res.rbp.get_parameter_attributes_as_list("estimated_value"))
+    obs_deg = x.copy()
+    obs_deg[:3] *= 180 / np.pi
+    res2 = sb.register(X_fix, X_mov, correspondences=100_000, rbp_observed_values=tuple(obs_deg),
+                       normals=None)
+    assert np.linalg.norm(res2.H - res.H) < 1e-6
