@@ -172,8 +172,23 @@ int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out /*
 typedef struct {
   double upload_ms, grid_mov_ms, grid_fix_ms, overlap_ms, normals_ms, match_ms, reject_solve_ms,
       transform_ms;
+  int64_t kernel_launches; /* kernels of this library launched on this context so far           */
 } sicp_timings;
 int32_t sicp_get_timings(sicp_ctx* ctx, sicp_timings* t /*[h]*/);
+
+/* Measurement hook: run `reps` iterations from the current device state and return the average
+ * device time (CUDA events on the context's stream) of each kernel group, in milliseconds:
+ * ms[0] grid match kernel, ms[1] brute-force pass (launched, usually empty), ms[2] reject+solve
+ * kernel, ms[3] whole iteration.  flush_l2 != 0 overwrites a 256 MiB scratch buffer before every
+ * iteration (outside the timed intervals) so each one starts with a cold L2.                    */
+int32_t sicp_time_stages(sicp_ctx* ctx, const sicp_run_params* p, int32_t reps, int32_t flush_l2,
+                         double ms[4] /*[h]*/);
+/* Diagnostics: %globaltimer stamps block 0 took in the last reject+solve kernel, microseconds
+ * relative to kernel entry.  [1] median done, [2] MAD done, [3] moments accumulated, [4] grid
+ * barrier passed, [5] LM solve done, [6] barrier, [7] residual pass, [8] barrier, [9] exit;
+ * [10..12] / [14..16] radix levels done / gather barrier / sort done for the median / MAD;
+ * [24],[25] radix levels used, [26],[27] candidates sorted (raw counts, not times).            */
+int32_t sicp_get_phase_times(sicp_ctx* ctx, double us[32] /*[h]*/);
 
 #ifdef __cplusplus
 }

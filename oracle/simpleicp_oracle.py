@@ -286,6 +286,8 @@ class Trace:
     iterations: List[IterationTrace] = field(default_factory=list)
     sigma: Optional[np.ndarray] = None
     timings: Dict[str, float] = field(default_factory=dict)
+    iter_seconds: List[float] = field(default_factory=list)  # wall time of each iteration
+    light: bool = False  # True: keep only timings (no per-iteration arrays)
 
 
 def simpleicp(
@@ -369,6 +371,7 @@ def simpleicp(
     it = -1
     for it in range(max_iterations):  # simpleicp.py:184
         H_in = H
+        t_it = time.perf_counter()
         if static_tree:
             q = transform_by_H(X_fix[idx_sel], np.linalg.inv(H))
             _, idx_nn = tree_static.query(q, k=1, p=2, workers=-1)
@@ -398,10 +401,14 @@ def simpleicp(
         H = rbp_to_H(x_est)
         residuals_all.append(res)
         if trace is not None:
-            trace.iterations.append(
-                IterationTrace(H_in, idx_nn, d, keep, med, mad, x_est.copy(), H.copy(), res, float(w))
-            )
-        if it > 0 and check_convergence_criteria(residuals_all[it], residuals_all[it - 1], min_change):
+            if not trace.light:
+                trace.iterations.append(
+                    IterationTrace(H_in, idx_nn, d, keep, med, mad, x_est.copy(), H.copy(), res, float(w))
+                )
+        stop = it > 0 and check_convergence_criteria(residuals_all[it], residuals_all[it - 1], min_change)
+        if trace is not None:
+            trace.iter_seconds.append(time.perf_counter() - t_it)
+        if stop:
             break
     t3 = time.perf_counter()
     sigma = estimate_parameter_uncertainties(res_w, jac, n_corr, w, w_obs)

@@ -26,7 +26,7 @@ SYMBOLS = (
     "sicp_set_clouds", "sicp_set_selected", "sicp_select_in_range", "sicp_estimate_normals",
     "sicp_set_normals", "sicp_get_knn", "sicp_match", "sicp_reject", "sicp_solve",
     "sicp_uncertainties", "sicp_run", "sicp_get_residuals", "sicp_iterate", "sicp_transform",
-    "sicp_get_timings",
+    "sicp_get_timings", "sicp_time_stages", "sicp_get_phase_times",
 )
 
 
@@ -56,7 +56,7 @@ class RunResult(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("upload_ms", "grid_mov_ms", "grid_fix_ms", "overlap_ms",
                                           "normals_ms", "match_ms", "reject_solve_ms",
-                                          "transform_ms")]
+                                          "transform_ms")] + [("kernel_launches", C.c_int64)]
 
 
 class SicpError(RuntimeError):
@@ -105,6 +105,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "sicp_iterate": [vp, C.POINTER(RunParams), C.POINTER(dbl), C.POINTER(IterRecord)],
         "sicp_transform": [vp, C.POINTER(dbl), vp],
         "sicp_get_timings": [vp, C.POINTER(Timings)],
+        "sicp_time_stages": [vp, C.POINTER(RunParams), i32, i32, C.POINTER(dbl)],
+        "sicp_get_phase_times": [vp, C.POINTER(dbl)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -326,6 +328,18 @@ class Engine:
             out = pinned_empty((self.n_mov, 3), np.float64)
         self._check(self._lib.sicp_transform(self._h, _d16(H), _ptr(out)))
         return out
+
+    def time_stages(self, params: RunParams, reps: int, flush_l2: bool) -> dict:
+        """Average device milliseconds per iteration of each kernel group (CUDA events)."""
+        ms = (C.c_double * 4)()
+        self._check(self._lib.sicp_time_stages(self._h, C.byref(params), int(reps), int(flush_l2), ms))
+        return {"match_grid": ms[0], "bruteforce_pass": ms[1], "reject_solve": ms[2], "iteration": ms[3]}
+
+    def phase_times(self) -> list:
+        """Diagnostics: block-0 phase stamps (us) of the last reject+solve kernel."""
+        us = (C.c_double * 32)()
+        self._check(self._lib.sicp_get_phase_times(self._h, us))
+        return list(us)
 
     def timings(self) -> dict:
         t = Timings()

@@ -491,7 +491,8 @@ int32_t sicp_iterate(sicp_ctx* ctx, const sicp_run_params* p, const double x_in[
     init_state(c, x_in, nullptr, true);
     ctx->it_counter = 0;
   }
-  match_launch(c, true, nullptr);
+  if (x_in) c.expect_unresolved = true;
+  match_launch(c, true, nullptr, nullptr, c.expect_unresolved);
   reject_solve_launch(c, *p, ctx->it_counter, true, false, 0);
   ctx->it_counter++;
   c.matched = c.rejected = true;
@@ -499,6 +500,7 @@ int32_t sicp_iterate(sicp_ctx* ctx, const sicp_run_params* p, const double x_in[
     fetch_records(c, 0, 1);
     sync(c);
     *rec = c.rec_host[0];
+    c.expect_unresolved = rec->n_bruteforce > 0;
   }
   API_END
 }
@@ -528,8 +530,9 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
   int done = 0, fetched = 0, converged = 0;
   DevState h;
   const int every = std::max(1, c.host_sync_every);
+  c.expect_unresolved = true;
   for (int it = 0; it < p->max_iterations; ++it) {
-    match_launch(c, true, nullptr);
+    match_launch(c, true, nullptr, nullptr, c.expect_unresolved);
     reject_solve_launch(c, *p, it, true, true, it);
     if ((it + 1) % every == 0 || it + 1 == p->max_iterations) {
       fetch_records(c, fetched, it + 1 - fetched);
@@ -537,6 +540,7 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
       sync(c);
       fetched = it + 1;
       done = h.iterations_done;
+      c.expect_unresolved = c.rec_host[it].n_bruteforce > 0;
       if (h.stop == 2 || (done < it + 1 && !h.stop)) {
         // an iteration ended with fewer than 6 correspondences
         const long long nk = c.rec_host[std::min(done, it)].n_kept;
@@ -610,6 +614,53 @@ int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out) {
     copy_any(c, mov_xyz_out, s, sizeof(double) * 3 * c.n_mov);
   }
   t.stop();
+  API_END
+}
+
+int32_t sicp_time_stages(sicp_ctx* ctx, const sicp_run_params* p, int32_t reps, int32_t flush_l2,
+                         double ms[4]) {
+  API_BEGIN(ctx)
+  require_normals(c);
+  SICP_REQUIRE(p && ms && reps >= 1, SICP_ERR_BAD_ARG, "bad argument");
+  const size_t kFlushBytes = 256ull << 20;
+  if (flush_l2) c.flush_buf.reserve(kFlushBytes);
+  cudaEvent_t e[4];
+  for (auto& ev : e) SICP_CUDA(cudaEventCreate(&ev));
+  double acc[4] = {0, 0, 0, 0};
+  for (int r = 0; r < reps; ++r) {
+    if (flush_l2) SICP_CUDA(cudaMemsetAsync(c.flush_buf.p, r & 0xff, kFlushBytes, c.stream));
+    SICP_CUDA(cudaEventRecord(e[0], c.stream));
+    match_launch(c, true, nullptr, e[1], c.expect_unresolved);
+    SICP_CUDA(cudaEventRecord(e[2], c.stream));
+    reject_solve_launch(c, *p, ctx->it_counter, true, false, 0);
+    SICP_CUDA(cudaEventRecord(e[3], c.stream));
+    SICP_CUDA(cudaEventSynchronize(e[3]));
+    ctx->it_counter++;
+    float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
+    cudaEventElapsedTime(&t01, e[0], e[1]);
+    cudaEventElapsedTime(&t12, e[1], e[2]);
+    cudaEventElapsedTime(&t23, e[2], e[3]);
+    cudaEventElapsedTime(&t03, e[0], e[3]);
+    acc[0] += t01;
+    acc[1] += t12;
+    acc[2] += t23;
+    acc[3] += t03;
+  }
+  for (auto& ev : e) cudaEventDestroy(ev);
+  for (int i = 0; i < 4; ++i) ms[i] = acc[i] / reps;
+  c.matched = c.rejected = true;
+  API_END
+}
+
+int32_t sicp_get_phase_times(sicp_ctx* ctx, double us[32]) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(us != nullptr, SICP_ERR_BAD_ARG, "us is NULL");
+  SICP_REQUIRE(c.phase_t.p != nullptr, SICP_ERR_STATE, "no reject/solve kernel has run");
+  unsigned long long t[32];
+  SICP_CUDA(cudaMemcpyAsync(t, c.phase_t.p, sizeof(t), cudaMemcpyDeviceToHost, c.stream));
+  sync(c);
+  for (int i = 0; i < 32; ++i)
+    us[i] = (i >= 24) ? (double)t[i] : ((t[i] >= t[0]) ? (double)(t[i] - t[0]) * 1e-3 : -1.0);
   API_END
 }
 

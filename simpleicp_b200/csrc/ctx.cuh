@@ -57,7 +57,7 @@ struct Ctx {
   int nn_engine = SICP_NN_AUTO;
   int sign_mode = SICP_SIGN_CANONICAL;
   double grid_target_occ = 3.0;
-  int grid_max_rings = 4;
+  int grid_max_rings = 8;
   int host_sync_every = 1;
 
   // clouds
@@ -88,6 +88,7 @@ struct Ctx {
   DevBuf<unsigned char> bf_scratch;
   long long n_kept = 0;
   bool matched = false, rejected = false, solved = false;
+  bool expect_unresolved = true;  // last known: did some query exceed the ring limit?
   double min_planarity_last = 0.0;
 
   // last solve state (for uncertainties)
@@ -101,6 +102,8 @@ struct Ctx {
   DevBuf<unsigned int> compact_sums;
   DevBuf<unsigned long long> bbox_keys;   // grid build scratch (kept apart from the select workspace)
   DevBuf<unsigned int> misc_counters;     // grid build / API scratch counters
+  DevBuf<unsigned char> flush_buf;        // 256 MiB scratch for cold-L2 measurements
+  DevBuf<unsigned long long> phase_t;     // %globaltimer stamps of the reject/solve kernel
   sicp_iter_record* rec_host = nullptr;  // pinned
   double* scal_host = nullptr;           // pinned staging for small reads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -118,7 +121,10 @@ void make_float4_copy(Ctx& c);
 // If out_d2 != nullptr the squared NN distance is written instead of the plane distance epilogue
 // being required (overlap filter).
 // The transform is read from c.dev_state (T, Tinv) on the device.
-void match_launch(Ctx& c, bool with_distance, double* out_d2);
+// allow_bf: bound the ring expansion by grid_max_rings and answer the rest with the brute-force
+// pass; otherwise the grid search runs to completion on its own (no extra launches).
+void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid = nullptr,
+                  bool allow_bf = true);
 void set_state_transform(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_loop);
 void estimate_normals_launch(Ctx& c, int k);
 void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve, bool arm_stop,

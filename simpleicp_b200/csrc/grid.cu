@@ -293,6 +293,7 @@ void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
     k_scan_blocksums<<<1, 1024, 0, st>>>(g.block_sums.p, (int)nsb);
     k_scan_down<<<(unsigned)nsb, 256, 0, st>>>(g.fill.p, g.n_cells, g.block_sums.p, g.cell_start.p);
     k_scan_total<<<1, 32, 0, st>>>(g.fill.p, g.n_cells, g.cell_start.p);
+    c.tm.kernel_launches += 5;
     unsigned int nocc = 0;
     SICP_CUDA(cudaMemcpyAsync(&nocc, c.misc_counters.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     SICP_CUDA(cudaStreamSynchronize(st));
@@ -313,6 +314,7 @@ void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
   k_sort_cells<<<(unsigned)((g.n_cells + 255) / 256), 256, 0, st>>>(g.cell_start.p, g.n_cells,
                                                                    g.recs.p);
   SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 5;  // bbox x3, scatter, sort_cells
   g.built = true;
 }
 
@@ -329,6 +331,7 @@ void make_float4_copy(Ctx& c) {
   k_float4_copy<<<(unsigned)((n_pad + 255) / 256), 256, 0, c.stream>>>(
       c.mov_xyz.p, c.n_mov, n_pad, c.mov_center[0], c.mov_center[1], c.mov_center[2], c.mov_f4.p);
   SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
 }
 
 }  // namespace sicp

@@ -386,6 +386,7 @@ void gather_queries_launch(Ctx& c) {
   k_gather_queries<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(c.fix_xyz.p, c.sel_idx.p,
                                                                        c.K, c.q_xyz.p);
   SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
 }
 
 // Brute-force pass over either the unresolved list (qlist != nullptr) or all K queries.
@@ -420,9 +421,10 @@ static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
       partials, n_chunks, q_total, qlist, qcount, c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p,
       with_distance ? 1 : 0, c.nn_idx.p, out);
   SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 2;
 }
 
-void match_launch(Ctx& c, bool with_distance, double* out_d2) {
+void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, bool allow_bf) {
   const long long K = c.K;
   c.nn_idx.reserve(K);
   c.dist.reserve(K);
@@ -430,15 +432,19 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2) {
   double* out = with_distance ? c.dist.p : out_d2;
   if (c.nn_engine == SICP_NN_BRUTE) {
     bf_launch(c, with_distance, out, true);
+    if (mid) SICP_CUDA(cudaEventRecord(mid, c.stream));
     return;
   }
   SICP_CUDA(cudaMemsetAsync(c.unresolved.p + K, 0, sizeof(unsigned int), c.stream));
-  const int rmax = (c.nn_engine == SICP_NN_GRID) ? (1 << 30) : c.grid_max_rings;
+  const bool use_bf = (c.nn_engine == SICP_NN_AUTO) && allow_bf;
+  const int rmax = use_bf ? c.grid_max_rings : (1 << 30);
   k_match_grid<<<(unsigned)((K + 127) / 128), 128, 0, c.stream>>>(
       c.gmov.view(), c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p, K, rmax, with_distance ? 1 : 0,
       c.nn_idx.p, out, c.unresolved.p);
   SICP_CUDA(cudaGetLastError());
-  if (c.nn_engine == SICP_NN_AUTO) bf_launch(c, with_distance, out, false);
+  c.tm.kernel_launches += 1;
+  if (mid) SICP_CUDA(cudaEventRecord(mid, c.stream));
+  if (use_bf) bf_launch(c, with_distance, out, false);
 }
 
 }  // namespace sicp

@@ -160,6 +160,7 @@ void estimate_normals_launch(Ctx& c, int k) {
       c.gfix.view(), c.fix_xyz.p, c.q_xyz.p, c.K, k, c.sign_mode, c.q_nrm.p, c.knn_idx.p,
       c.knn_d2.p);
   SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
 }
 
 }  // namespace sicp

@@ -37,7 +37,7 @@ constexpr int RS_THREADS = 384;  // 12 warps = 3 accumulation roles x 4 warps
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_BINS = 2048;
 constexpr int RS_LEVELS = 6;
-constexpr int RS_CAP = 2048;
+constexpr int RS_CAP = 2048;       // candidate buffer (last two slots carry the selected keys)
 constexpr int RS_NACC = 26;           // accumulators per role
 constexpr int RS_NPART = 3 * RS_NACC; // partial sums per block in phase C
 
@@ -65,6 +65,15 @@ struct Shared {
   double g[6];
   double F;
   double tot[RS_NPART];
+  double Ak[36];
+  double gk[6];
+  double delta[6];
+  int spd;
+  // in-block refinement of the selected radix bin
+  unsigned int h256[256];
+  unsigned long long small[64];
+  unsigned long long sel_above;
+  unsigned int small_n;
 };
 
 template <bool MULTI>
@@ -122,23 +131,107 @@ __device__ unsigned int find_bin(Shared& s, const unsigned int* __restrict__ ghi
   return (unsigned int)s.bc[7];
 }
 
-__device__ void bitonic_sort(unsigned long long* a, int n_pow2) {
-  for (int k = 2; k <= n_pow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < n_pow2; t += RS_THREADS) {
-        const int p = t ^ j;
-        if (p > t) {
-          const unsigned long long x = a[t], y = a[p];
-          const bool up = ((t & k) == 0);
-          if ((x > y) == up) {
-            a[t] = y;
-            a[p] = x;
+// In-block refinement: keys[0..cnt) agree on every bit above `shift`; find the k-th smallest
+// (0-based) and its successor (`above` when the k-th is the largest).  8-bit radix passes over
+// the shared-memory candidates (__syncthreads only) until <= 32 remain, then one warp ranks
+// them.  Duplicates are handled (all 64 bits fixed -> every remaining candidate is equal).
+__device__ void block_select(Shared& s, const unsigned long long* keys, int cnt, unsigned int k,
+                             int shift, unsigned long long above, unsigned long long& klo,
+                             unsigned long long& khi) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned long long lowmask = (1ull << shift) - 1ull;  // shift <= 53 here
+  unsigned long long prefix = 0;
+  int bits = shift;
+  unsigned int n = (unsigned int)cnt;
+  if (tid == 0) s.sel_above = above;
+  __syncthreads();
+  while (n > 32u && bits > 0) {
+    const int w = min(8, bits), sh = bits - w;
+    if (tid < 256) s.h256[tid] = 0;
+    __syncthreads();
+    for (int t = tid; t < cnt; t += RS_THREADS) {
+      const unsigned long long low = keys[t] & lowmask;
+      if (bits == shift || (low >> bits) == prefix)
+        atomicAdd(&s.h256[(unsigned int)(low >> sh) & ((1u << w) - 1u)], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      unsigned int v[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = s.h256[lane * 8 + j];
+        sum += v[j];
+      }
+      unsigned int incl = sum;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t2;
+      }
+      unsigned int run = incl - sum;
+      if (k >= run && k < run + sum) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (k < run + v[j]) {
+            s.k = k - run;
+            s.cnt = v[j];
+            s.bc[7] = (double)(lane * 8 + j);
+            break;
           }
+          run += v[j];
         }
       }
-      __syncthreads();
     }
+    __syncthreads();
+    const unsigned int bin = (unsigned int)s.bc[7];
+    k = s.k;
+    n = s.cnt;
+    if (k + 1u >= n) {
+      // the successor may lie outside the chosen bin: smallest active key with a larger digit
+      unsigned long long mymin = ~0ull;
+      for (int t = tid; t < cnt; t += RS_THREADS) {
+        const unsigned long long low = keys[t] & lowmask;
+        if ((bits == shift || (low >> bits) == prefix) &&
+            ((unsigned int)(low >> sh) & ((1u << w) - 1u)) > bin)
+          mymin = min(mymin, keys[t]);
+      }
+      for (int o = 16; o > 0; o >>= 1) mymin = min(mymin, __shfl_xor_sync(0xffffffffu, mymin, o));
+      if (lane == 0 && mymin != ~0ull) atomicMin(&s.sel_above, mymin);
+    }
+    prefix = (prefix << w) | bin;
+    bits = sh;
+    __syncthreads();
   }
+  if (tid == 0) s.small_n = 0;
+  __syncthreads();
+  if (n > 32u) {
+    // all low bits fixed and still more than 32 candidates: they are all the same key
+    for (int t = tid; t < cnt; t += RS_THREADS)
+      if (((keys[t] & lowmask) >> bits) == prefix) s.small[0] = keys[t];
+    __syncthreads();
+    klo = s.small[0];
+    khi = (k + 1u < n) ? klo : s.sel_above;
+    __syncthreads();
+    return;
+  }
+  for (int t = tid; t < cnt; t += RS_THREADS) {
+    const unsigned long long low = keys[t] & lowmask;
+    if (bits == shift || (low >> bits) == prefix) s.small[atomicAdd(&s.small_n, 1u)] = keys[t];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const unsigned long long key = (lane < (int)n) ? s.small[lane] : ~0ull;
+    unsigned int r = 0;
+    for (unsigned int j = 0; j < n; ++j) {
+      const unsigned long long kj = s.small[j];
+      r += (kj < key || (kj == key && (int)j < lane)) ? 1u : 0u;
+    }
+    if (lane < (int)n && r == k) s.sortbuf[RS_CAP - 2] = key;
+    if (lane < (int)n && r == k + 1u) s.sortbuf[RS_CAP - 1] = key;
+  }
+  __syncthreads();
+  klo = s.sortbuf[RS_CAP - 2];
+  khi = (k + 1u < n) ? s.sortbuf[RS_CAP - 1] : s.sel_above;
+  __syncthreads();
 }
 
 // Median of {keyfn(i) : i in S1} with NumPy semantics.  SEL = 0: keys of d; SEL = 1: keys of
@@ -192,14 +285,19 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     cnt = s.cnt;
     prefix = (prefix << width) | bin;
     __syncthreads();
-    if (cnt <= RS_CAP || level == RS_LEVELS - 1) break;
+    if (cnt <= RS_CAP - 2 || level == RS_LEVELS - 1) break;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    wk.phase_t[10 + SEL * 4] = global_timer_ns();
+    wk.phase_t[24 + SEL] = (unsigned long long)(level + 1);
+    wk.phase_t[26 + SEL] = (unsigned long long)cnt;
   }
   // ---- gather the candidates of the selected bin; track the smallest key above it
   const int shift = kShift[level];
   unsigned long long* cand = wk.cand + (size_t)SEL * RS_CAP;
   unsigned int* ccount = wk.counters + SEL;
   unsigned long long* gmin = wk.minkey + SEL;
-  const bool gather = (cnt <= RS_CAP);
+  const bool gather = (cnt <= RS_CAP - 2);
   unsigned long long mymin = ~0ull;
   if (!MULTI) {
     if (threadIdx.x == 0) s.total = 0;
@@ -238,26 +336,22 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     }
   }
   gsync<MULTI>();
+  if (blockIdx.x == 0 && threadIdx.x == 0) wk.phase_t[11 + SEL * 4] = global_timer_ns();
   const unsigned long long above = MULTI ? *gmin : wmin[0];
   unsigned long long klo, khi;
   if (gather) {
-    int np2 = 32;
-    while (np2 < (int)cnt) np2 <<= 1;
-    if (MULTI)
-      for (int t = threadIdx.x; t < np2; t += RS_THREADS) s.sortbuf[t] = (t < (int)cnt) ? cand[t] : ~0ull;
-    else
-      for (int t = threadIdx.x; t < np2; t += RS_THREADS)
-        if (t >= (int)cnt) s.sortbuf[t] = ~0ull;
-    __syncthreads();
-    bitonic_sort(s.sortbuf, np2);
-    klo = s.sortbuf[k];
-    khi = (k + 1 < cnt) ? s.sortbuf[k + 1] : above;
+    if (MULTI) {
+      for (int t = threadIdx.x; t < (int)cnt; t += RS_THREADS) s.sortbuf[t] = cand[t];
+      __syncthreads();
+    }
+    block_select(s, s.sortbuf, (int)cnt, k, shift, above, klo, khi);
   } else {
     // only reachable when all 64 key bits are fixed: every candidate equals the prefix
     klo = prefix;
     khi = (k + 1 < cnt) ? prefix : above;
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) wk.phase_t[12 + SEL * 4] = global_timer_ns();
   if (threadIdx.x == 0) {
     s.bc[0] = key_to_f64(klo);
     s.bc[1] = even ? key_to_f64(khi) : key_to_f64(klo);
@@ -268,12 +362,17 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
 
 // --- Levenberg-Marquardt on the 13 x 13 moment matrix (warp 0 of block 0) -------------------
 // theta(x) = [R(alpha) row-wise with t'_a after each row, 1], t' = R c_m + t - c_f.
+// Everything here is a serial dependency chain executed by ONE warp while the rest of the grid
+// waits at a barrier, so the code is organised to keep that chain short: the three sincos run on
+// three lanes, the matrix products are spread over the lanes, and the 6 x 6 factorisation is a
+// fully unrolled register Cholesky (one rsqrt per pivot, no division, no local memory).
 __device__ void lm_eval(Shared& s, const double* x, const double* cm, const double* cf, int lane) {
+  double sn = 0.0, cs = 1.0;
+  if (lane < 3) sincos(x[lane], &sn, &cs);
+  const double s1 = __shfl_sync(0xffffffffu, sn, 0), c1 = __shfl_sync(0xffffffffu, cs, 0);
+  const double s2 = __shfl_sync(0xffffffffu, sn, 1), c2 = __shfl_sync(0xffffffffu, cs, 1);
+  const double s3 = __shfl_sync(0xffffffffu, sn, 2), c3 = __shfl_sync(0xffffffffu, cs, 2);
   if (lane == 0) {
-    double s1, c1, s2, c2, s3, c3;
-    sincos(x[0], &s1, &c1);
-    sincos(x[1], &s2, &c2);
-    sincos(x[2], &s3, &c3);
     double R[9], D[3][9];
     R[0] = c2 * c3; R[1] = -c2 * s3; R[2] = s2;
     R[3] = c1 * s3 + s1 * s2 * c3; R[4] = c1 * c3 - s1 * s2 * s3; R[5] = -s1 * c2;
@@ -290,24 +389,32 @@ __device__ void lm_eval(Shared& s, const double* x, const double* cm, const doub
     D[2][0] = -c2 * s3; D[2][1] = -c2 * c3; D[2][2] = 0;
     D[2][3] = c1 * c3 - s1 * s2 * s3; D[2][4] = -c1 * s3 - s1 * s2 * c3; D[2][5] = 0;
     D[2][6] = s1 * c3 + c1 * s2 * s3; D[2][7] = -s1 * s3 + c1 * s2 * c3; D[2][8] = 0;
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
+#pragma unroll
       for (int b = 0; b < 3; ++b) {
         s.th[a * 4 + b] = R[a * 3 + b];
+#pragma unroll
         for (int k = 0; k < 3; ++k) s.J[a * 4 + b][k] = D[k][a * 3 + b];
+#pragma unroll
         for (int k = 3; k < 6; ++k) s.J[a * 4 + b][k] = 0.0;
       }
       s.th[a * 4 + 3] = R[a * 3 + 0] * cm[0] + R[a * 3 + 1] * cm[1] + R[a * 3 + 2] * cm[2] + x[3 + a] - cf[a];
+#pragma unroll
       for (int k = 0; k < 3; ++k)
         s.J[a * 4 + 3][k] = D[k][a * 3 + 0] * cm[0] + D[k][a * 3 + 1] * cm[1] + D[k][a * 3 + 2] * cm[2];
+#pragma unroll
       for (int k = 3; k < 6; ++k) s.J[a * 4 + 3][k] = (k - 3 == a) ? 1.0 : 0.0;
     }
     s.th[12] = 1.0;
+#pragma unroll
     for (int k = 0; k < 6; ++k) s.J[12][k] = 0.0;
   }
   __syncwarp();
   for (int e = lane; e < 91; e += 32) {
     const int r = e / 7, c = e % 7;
     double acc = 0.0;
+#pragma unroll
     for (int m = 0; m < 13; ++m) acc = fma(s.M[r][m], (c < 6) ? s.J[m][c] : s.th[m], acc);
     s.B[r][c] = acc;
   }
@@ -316,13 +423,16 @@ __device__ void lm_eval(Shared& s, const double* x, const double* cm, const doub
     double acc = 0.0;
     if (e < 36) {
       const int i = e / 6, j = e % 6;
+#pragma unroll
       for (int m = 0; m < 13; ++m) acc = fma(s.J[m][i], s.B[m][j], acc);
       s.A[e] = acc;
     } else if (e < 42) {
       const int i = e - 36;
+#pragma unroll
       for (int m = 0; m < 13; ++m) acc = fma(s.J[m][i], s.B[m][6], acc);
       s.g[i] = acc;
     } else {
+#pragma unroll
       for (int m = 0; m < 13; ++m) acc = fma(s.th[m], s.B[m][6], acc);
       s.F = acc;
     }
@@ -330,140 +440,195 @@ __device__ void lm_eval(Shared& s, const double* x, const double* cm, const doub
   __syncwarp();
 }
 
-// In-place Cholesky solve of the n x n SPD system A x = b (n <= 6), returns false if not SPD.
-__device__ bool chol_solve(double* A, double* b, int n) {
-  for (int j = 0; j < n; ++j) {
+// Fully unrolled 6 x 6 Cholesky solve in registers.  A is row-major symmetric positive definite
+// (rows/columns of fixed parameters are identity), b is overwritten with the solution.
+__device__ __forceinline__ bool chol6_solve(const double (&A)[36], double (&b)[6]) {
+  double L[21], inv[6];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
     double d = A[j * 6 + j];
-    for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
-    if (!(d > 0.0)) return false;
-    d = sqrt(d);
-    A[j * 6 + j] = d;
-    for (int i = j + 1; i < n; ++i) {
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fma(-L[j * (j + 1) / 2 + k], L[j * (j + 1) / 2 + k], d);
+    ok = ok && (d > 0.0) && isfinite(d);
+    const double r = rsqrt(d);
+    inv[j] = r;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
       double v = A[i * 6 + j];
-      for (int k = 0; k < j; ++k) v -= A[i * 6 + k] * A[j * 6 + k];
-      A[i * 6 + j] = v / d;
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-L[i * (i + 1) / 2 + k], L[j * (j + 1) / 2 + k], v);
+      L[i * (i + 1) / 2 + j] = v * r;
     }
   }
-  for (int i = 0; i < n; ++i) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
     double v = b[i];
-    for (int k = 0; k < i; ++k) v -= A[i * 6 + k] * b[k];
-    b[i] = v / A[i * 6 + i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v = fma(-L[i * (i + 1) / 2 + k], b[k], v);
+    b[i] = v * inv[i];
   }
-  for (int i = n - 1; i >= 0; --i) {
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
     double v = b[i];
-    for (int k = i + 1; k < n; ++k) v -= A[k * 6 + i] * b[k];
-    b[i] = v / A[i * 6 + i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v = fma(-L[k * (k + 1) / 2 + i], b[k], v);
+    b[i] = v * inv[i];
   }
-  return true;
+  return ok;
 }
 
 struct LmOut {
   double x[6];
-  double An[36];  // unweighted J^T M J at the solution
   int iters;
   int ok;
 };
 
+// s.Ak / s.gk hold the unweighted J^T M J and J^T M theta at the current x.
 __device__ void lm_solve(Shared& s, const RSArgs& a, double w, const double* x0, const double* cm,
                          const double* cf, LmOut& out, int lane) {
   double x[6], xn[6];
-  for (int j = 0; j < 6; ++j) x[j] = x0[j];
-  int fidx[6], nf = 0;
-  for (int j = 0; j < 6; ++j)
-    if (isfinite(a.wobs[j])) fidx[nf++] = j;
+  bool fre[6], obsd[6];
+  int nf = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    x[j] = x0[j];
+    fre[j] = isfinite(a.wobs[j]);
+    obsd[j] = fre[j] && a.wobs[j] > 0.0;
+    nf += fre[j] ? 1 : 0;
+  }
   const double w2 = w * w;
   auto obs_cost = [&](const double* xx) {
     double c = 0.0;
+#pragma unroll
     for (int j = 0; j < 6; ++j)
-      if (a.wobs[j] > 0.0 && isfinite(a.wobs[j])) {
+      if (obsd[j]) {
         const double r = a.wobs[j] * (xx[j] - a.obs[j]);
         c += r * r;
       }
     return c;
   };
+  auto keep_eval = [&]() {
+    for (int e = lane; e < 42; e += 32) {
+      if (e < 36) s.Ak[e] = s.A[e];
+      else s.gk[e - 36] = s.g[e - 36];
+    }
+    __syncwarp();
+  };
   lm_eval(s, x, cm, cf, lane);
+  keep_eval();
   double F = w2 * s.F + obs_cost(x);
   double lambda = 0.0;
   int it = 0, ok = 1;
-  double Ak[36], gk[6];
-  for (int e = 0; e < 36; ++e) Ak[e] = s.A[e];
-  for (int e = 0; e < 6; ++e) gk[e] = s.g[e];
   for (it = 0; it < 40 && nf > 0; ++it) {
-    // reduced, weighted Gauss-Newton system on the free parameters
-    double Ar[36], br[6];
-    for (int i = 0; i < nf; ++i) {
-      const int pi = fidx[i];
-      double gi = w2 * gk[pi];
-      if (a.wobs[pi] > 0.0) gi += a.wobs[pi] * a.wobs[pi] * (x[pi] - a.obs[pi]);
-      br[i] = -gi;
-      for (int j = 0; j < nf; ++j) Ar[i * 6 + j] = w2 * Ak[pi * 6 + fidx[j]];
-      if (a.wobs[pi] > 0.0) Ar[i * 6 + i] += a.wobs[pi] * a.wobs[pi];
-      Ar[i * 6 + i] *= (1.0 + lambda);
+    if (lane == 0) {
+      // weighted Gauss-Newton system; fixed parameters become identity rows (delta = 0)
+      double Ar[36], br[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          Ar[i * 6 + j] = (fre[i] && fre[j]) ? w2 * s.Ak[i * 6 + j] : ((i == j) ? 1.0 : 0.0);
+        double gi = fre[i] ? w2 * s.gk[i] : 0.0;
+        if (obsd[i]) {
+          gi += a.wobs[i] * a.wobs[i] * (x[i] - a.obs[i]);
+          Ar[i * 6 + i] += a.wobs[i] * a.wobs[i];
+        }
+        if (fre[i]) Ar[i * 6 + i] *= (1.0 + lambda);
+        br[i] = -gi;
+      }
+      const bool spd = chol6_solve(Ar, br);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) s.delta[i] = br[i];
+      s.spd = spd ? 1 : 0;
     }
-    const bool spd = chol_solve(Ar, br, nf);
-    if (!spd) {
+    __syncwarp();
+    if (!s.spd) {
       lambda = fmax(lambda * 10.0, 1e-6);
       if (lambda > 1e10) {
         ok = 0;
         break;
       }
+      __syncwarp();
       continue;
     }
     double rel = 0.0;
-    for (int j = 0; j < 6; ++j) xn[j] = x[j];
-    for (int i = 0; i < nf; ++i) {
-      xn[fidx[i]] = x[fidx[i]] + br[i];
-      rel = fmax(rel, fabs(br[i]) / fmax(fabs(x[fidx[i]]), 1e-3));
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const double dj = fre[j] ? s.delta[j] : 0.0;
+      xn[j] = x[j] + dj;
+      rel = fmax(rel, fabs(dj) / fmax(fabs(x[j]), 1e-3));
+    }
+    __syncwarp();
+    if (rel < 1e-9 && lambda == 0.0) {
+      // undamped Gauss-Newton step below 1e-9 relative: converged; take it without another
+      // evaluation (the reference's own solver stops at ftol = xtol = 1e-8)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) x[j] = xn[j];
+      ++it;
+      break;
     }
     lm_eval(s, xn, cm, cf, lane);
     const double Fn = w2 * s.F + obs_cost(xn);
-    if (Fn <= F * (1.0 + 1e-10) + 1e-300 || rel < 1e-12) {
-      const bool stalled = (it >= 1 && Fn >= F * (1.0 - 1e-14));
+    // Inside the basin (small undamped steps) plain Gauss-Newton is used: the cost, evaluated
+    // through the moment matrix, carries cancellation noise of ~1e-9 relative, too coarse to
+    // accept or reject steps that change it by less.  Far from it the cost test guards the step.
+    const bool in_basin = (lambda == 0.0 && rel < 1e-3);
+    if (in_basin || Fn <= F * (1.0 + 1e-10) + 1e-300) {
+#pragma unroll
       for (int j = 0; j < 6; ++j) x[j] = xn[j];
-      for (int e = 0; e < 36; ++e) Ak[e] = s.A[e];
-      for (int e = 0; e < 6; ++e) gk[e] = s.g[e];
+      keep_eval();
       F = Fn;
       lambda = (lambda > 1e-9) ? lambda * 0.1 : 0.0;
-      if (rel < 1e-11 || stalled) {
-        ++it;
-        break;
-      }
     } else {
       lambda = fmax(lambda * 10.0, 1e-4);
       if (lambda > 1e10) break;
     }
   }
+#pragma unroll
   for (int j = 0; j < 6; ++j) out.x[j] = x[j];
-  for (int e = 0; e < 36; ++e) out.An[e] = Ak[e];
   out.iters = it;
   out.ok = ok;
 }
 
 // sigma of the free parameters: Cxx = s0^2 (A^T P A)^-1 in the reference's formulation
 // (optimization.py:147-160): N = w * sum a a^T + diag(w_obs), vPv = w sum r^2 + sum w_obs dx^2.
+// Called by a full warp: lane j < 6 produces sigma[j] (one column of the inverse each).
 __device__ void uncertainties(const RSArgs& a, const double* An, double w, const double* x,
-                              double sum_r2, long long n_kept, double* sigma) {
-  int fidx[6], nf = 0, nobs = 0;
+                              double sum_r2, long long n_kept, int lane, double* sigma) {
+  if (lane >= 6) return;
+  int nf = 0, nobs = 0;
+  bool fre[6];
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
-    sigma[j] = nan("");
-    if (isfinite(a.wobs[j])) fidx[nf++] = j;
-    if (a.wobs[j] > 0.0 && isfinite(a.wobs[j])) ++nobs;
+    fre[j] = isfinite(a.wobs[j]);
+    nf += fre[j] ? 1 : 0;
+    nobs += (fre[j] && a.wobs[j] > 0.0) ? 1 : 0;
   }
-  if (nf == 0) return;
   double vPv = w * sum_r2;
+#pragma unroll
   for (int j = 0; j < 6; ++j)
-    if (a.wobs[j] > 0.0 && isfinite(a.wobs[j])) vPv += a.wobs[j] * (x[j] - a.obs[j]) * (x[j] - a.obs[j]);
-  const double dof = (double)(n_kept + nobs - nf);
-  const double s02 = vPv / dof;
-  for (int c = 0; c < nf; ++c) {
-    double N[36], e[6];
-    for (int i = 0; i < nf; ++i) {
-      for (int j = 0; j < nf; ++j) N[i * 6 + j] = w * An[fidx[i] * 6 + fidx[j]];
-      if (a.wobs[fidx[i]] > 0.0) N[i * 6 + i] += a.wobs[fidx[i]];
-      e[i] = (i == c) ? 1.0 : 0.0;
-    }
-    if (chol_solve(N, e, nf)) sigma[fidx[c]] = sqrt(s02 * e[c]);
+    if (fre[j] && a.wobs[j] > 0.0) vPv += a.wobs[j] * (x[j] - a.obs[j]) * (x[j] - a.obs[j]);
+  const double s02 = vPv / (double)(n_kept + nobs - nf);
+  double N[36], e[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      N[i * 6 + j] = (fre[i] && fre[j]) ? w * An[i * 6 + j] : ((i == j) ? 1.0 : 0.0);
+    if (fre[i] && a.wobs[i] > 0.0) N[i * 6 + i] += a.wobs[i];
+    e[i] = (i == lane) ? 1.0 : 0.0;
   }
+  const bool ok = chol6_solve(N, e);
+  double mine = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i == lane) mine = e[i];
+  bool is_free = false;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i == lane) is_free = fre[i];
+  sigma[lane] = (ok && is_free) ? sqrt(s02 * mine) : nan("");
 }
 
 template <bool MULTI>
@@ -485,6 +650,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     }
   }
   if (st->stop) return;  // a previous iteration already met the stop rule
+#define RS_STAMP(i) do { if (blockIdx.x == 0 && tid == 0) wk.phase_t[i] = global_timer_ns(); } while (0)
+  RS_STAMP(0);
 
   // ---- A: median
   unsigned int n1 = 0;
@@ -500,12 +667,14 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
   }
   const double median = 0.5 * (s.bc[0] + s.bc[1]);
   __syncthreads();
+  RS_STAMP(1);
   // ---- B: MAD
   unsigned int n1b = 0;
   radix_median<MULTI, 1>(s, a, wk, median, n1b);
   const double mad = 0.5 * (s.bc[0] + s.bc[1]);
   const double lim = 3.0 * mad;
   __syncthreads();
+  RS_STAMP(2);
 
   // ---- C: keep flags + moment accumulation
   const Rigid Tin = st->T;
@@ -518,17 +687,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     for (int j = 0; j < RS_NACC; ++j) acc[j] = 0.0;
     const long long chunk = (K + G - 1) / G;
     const long long i0 = blockIdx.x * chunk, i1 = min(i0 + chunk, K);
-    for (long long i = i0 + sub; i < i1; i += 128) {
-      const float4 nr = a.q_nrm[i];
-      const double d = a.dist[i];
-      const bool kp = ((double)nr.w >= a.min_planarity) && (fabs(d - median) <= lim);
-      if (role == 0) a.keep[i] = kp ? 1 : 0;
-      if (!kp) continue;
-      const long long j = a.nn_idx[i];
-      const double u0 = a.mov_xyz[3 * j + 0] - cm[0], u1 = a.mov_xyz[3 * j + 1] - cm[1],
-                   u2 = a.mov_xyz[3 * j + 2] - cm[2];
-      const double q0 = a.q_xyz[3 * i + 0] - cf[0], q1 = a.q_xyz[3 * i + 1] - cf[1],
-                   q2 = a.q_xyz[3 * i + 2] - cf[2];
+    const float4* __restrict__ qn = a.q_nrm;
+    const double* __restrict__ dd = a.dist;
+    const long long* __restrict__ nn = a.nn_idx;
+    const double* __restrict__ mv = a.mov_xyz;
+    const double* __restrict__ qx = a.q_xyz;
+    auto accumulate = [&](const float4 nr, const double d, const double p0, const double p1,
+                          const double p2, const double f0, const double f1, const double f2) {
+      const double u0 = p0 - cm[0], u1 = p1 - cm[1], u2 = p2 - cm[2];
+      const double q0 = f0 - cf[0], q1 = f1 - cf[1], q2 = f2 - cf[2];
       const double n0 = (double)nr.x, n1d = (double)nr.y, n2 = (double)nr.z;
       const double sc = -(n0 * q0 + n1d * q1 + n2 * q2);
       double na, nb, nv;
@@ -557,6 +724,28 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
         acc[24] += d;
         acc[25] = fma(d, d, acc[25]);
       }
+    };
+    // two elements per trip so that both dependent gather chains (nn_idx -> mov_xyz) overlap
+    for (long long i = i0 + sub; i < i1; i += 256) {
+      const long long ib = i + 128;
+      const bool hb = ib < i1;
+      const float4 nrA = qn[i];
+      const float4 nrB = hb ? qn[ib] : make_float4(0.f, 0.f, 0.f, -1.f);
+      const double dA = dd[i], dB = hb ? dd[ib] : 0.0;
+      const bool kA = ((double)nrA.w >= a.min_planarity) && (fabs(dA - median) <= lim);
+      const bool kB = hb && ((double)nrB.w >= a.min_planarity) && (fabs(dB - median) <= lim);
+      const long long jA = kA ? nn[i] : 0, jB = kB ? nn[ib] : 0;
+      const long long ia = kA ? i : i0, ibb = kB ? ib : i0;
+      const double pA0 = mv[3 * jA + 0], pA1 = mv[3 * jA + 1], pA2 = mv[3 * jA + 2];
+      const double pB0 = mv[3 * jB + 0], pB1 = mv[3 * jB + 1], pB2 = mv[3 * jB + 2];
+      const double fA0 = qx[3 * ia + 0], fA1 = qx[3 * ia + 1], fA2 = qx[3 * ia + 2];
+      const double fB0 = qx[3 * ibb + 0], fB1 = qx[3 * ibb + 1], fB2 = qx[3 * ibb + 2];
+      if (kA) accumulate(nrA, dA, pA0, pA1, pA2, fA0, fA1, fA2);
+      if (kB) accumulate(nrB, dB, pB0, pB1, pB2, fB0, fB1, fB2);
+      if (role == 0) {
+        a.keep[i] = kA ? 1 : 0;
+        if (hb) a.keep[ib] = kB ? 1 : 0;
+      }
     }
 #pragma unroll
     for (int j = 0; j < RS_NACC; ++j) {
@@ -569,23 +758,46 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       double v = 0.0;
       for (int ww = r; ww < RS_WARPS; ww += 3) v += s.red[ww][j];
       if (MULTI)
-        wk.partials[(size_t)blockIdx.x * RS_NPART + tid] = v;
+        wk.partials[(size_t)tid * G + blockIdx.x] = v;
       else
         s.tot[tid] = v;
     }
   }
+  RS_STAMP(3);
   gsync<MULTI>();
+  RS_STAMP(4);
 
   // ---- D: block 0 reduces the partials and solves
   if (blockIdx.x == 0) {
     if (MULTI) {
-      if (tid < RS_NPART) {
+      // fixed-order sum of the per-block partials, stored value-major ([value][block]): each warp
+      // owns a few values, reads their G block entries with coalesced, fully overlapped loads and
+      // finishes with a shuffle tree (deterministic: the order depends on G only)
+      // (all loads of a warp are issued before the first use: one L2 round trip, not 35)
+      constexpr int NO = (RS_NPART + RS_WARPS - 1) / RS_WARPS;  // values per warp
+      constexpr int NB = 8;                                      // 32 * 8 = 256 blocks max
+      double r[NO][NB];
+#pragma unroll
+      for (int q = 0; q < NO; ++q) {
+        const int o = warp + q * RS_WARPS;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const int b = lane + 32 * u;
+          r[q][u] = (o < RS_NPART && b < G) ? wk.partials[(size_t)o * G + b] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NO; ++q) {
+        const int o = warp + q * RS_WARPS;
         double v = 0.0;
-        for (int b = 0; b < G; ++b) v += wk.partials[(size_t)b * RS_NPART + tid];
-        s.tot[tid] = v;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) v += r[q][u];
+        v = warp_sum(v);
+        if (lane == 0 && o < RS_NPART) s.tot[o] = v;
       }
     }
     __syncthreads();
+    RS_STAMP(17);
     // assemble M (13 x 13) from T (6 x 10), V (3 x 4), S
     for (int e = tid; e < 169; e += RS_THREADS) {
       const int r = e / 13, c = e % 13;
@@ -606,6 +818,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       s.M[r][c] = v;
     }
     __syncthreads();
+    RS_STAMP(18);
     if (warp == 0) {
       const long long n_kept = (long long)(s.tot[0 * RS_NACC + 25] + 0.5);
       const double sum_d = s.tot[1 * RS_NACC + 24], sum_d2 = s.tot[1 * RS_NACC + 25];
@@ -622,6 +835,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       lo.ok = 1;
       if (!skip) {
         lm_solve(s, a, w, st->x, cm, cf, lo, lane);
+        if (lane == 0) wk.phase_t[19] = global_timer_ns();
       }
       if (lane == 0) {
         rec->n_kept = n_kept;
@@ -638,14 +852,16 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
         if (n_kept < 6 && a.do_solve && a.arm_stop) st->stop = 2;  // too few correspondences
         if (!skip) {
           for (int j = 0; j < 6; ++j) st->x_new[j] = lo.x[j];
-          for (int e = 0; e < 36; ++e) st->An[e] = lo.An[e];
+          for (int e = 0; e < 36; ++e) st->An[e] = s.Ak[e];
           st->T_new = rigid_from_x(lo.x);
           st->lm_ok = lo.ok;
         }
       }
     }
   }
+  RS_STAMP(5);
   gsync<MULTI>();
+  RS_STAMP(6);
   if (st->skip) return;
 
   // ---- E: residuals at the solution, in the reference's operation order
@@ -687,14 +903,26 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       }
     }
   }
+  RS_STAMP(7);
   gsync<MULTI>();
-  if (blockIdx.x == 0 && tid == 0) {
+  RS_STAMP(8);
+  if (blockIdx.x == 0 && warp == 0) {
     double t0 = 0, t1 = 0;
     if (MULTI) {
-      for (int b = 0; b < G; ++b) {
-        t0 += wk.partials[(size_t)G * RS_NPART + 2 * b + 0];
-        t1 += wk.partials[(size_t)G * RS_NPART + 2 * b + 1];
+      double r0[8], r1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = lane + 32 * u;
+        r0[u] = (b < G) ? wk.partials[(size_t)G * RS_NPART + 2 * b + 0] : 0.0;
+        r1[u] = (b < G) ? wk.partials[(size_t)G * RS_NPART + 2 * b + 1] : 0.0;
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        t0 += r0[u];
+        t1 += r1[u];
+      }
+      t0 = warp_sum(t0);
+      t1 = warp_sum(t1);
     } else {
       t0 = s.bc[2];
       t1 = s.bc[3];
@@ -702,30 +930,32 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     const long long n = st->n_kept;
     const double mean = t0 / (double)n;
     const double sd = sqrt(fmax(t1 / (double)n - mean * mean, 0.0));
-    rec->mean_res = mean;
-    rec->std_res = sd;
-    double sigma[6];
-    uncertainties(a, st->An, st->w, st->x_new, t1, n, sigma);
-    for (int j = 0; j < 6; ++j) {
-      rec->x[j] = st->x_new[j];
-      st->sigma[j] = sigma[j];
-      st->x[j] = st->x_new[j];
+    // one lane per parameter: sigma_j, and the new cumulative parameters
+    uncertainties(a, st->An, st->w, st->x_new, t1, n, lane, st->sigma);
+    if (lane < 6) {
+      rec->x[lane] = st->x_new[lane];
+      st->x[lane] = st->x_new[lane];
     }
-    st->T = st->T_new;
-    st->Tinv = rigid_inverse(st->T_new);
-    // stop rule (simpleicp.py:355-379): relative change in percent of mean and population std
-    int stop = 0;
-    if (a.it > 0) {
-      const double m0 = st->prev_mean, s0 = st->prev_std;
-      const double cmn = (m0 == 0.0) ? ((mean == 0.0) ? 0.0 : kInf) : fabs((mean - m0) / m0 * 100.0);
-      const double csd = (s0 == 0.0) ? ((sd == 0.0) ? 0.0 : kInf) : fabs((sd - s0) / s0 * 100.0);
-      stop = (cmn < a.min_change && csd < a.min_change) ? 1 : 0;
+    if (lane == 0) {
+      rec->mean_res = mean;
+      rec->std_res = sd;
+      st->T = st->T_new;
+      st->Tinv = rigid_inverse(st->T_new);
+      // stop rule (simpleicp.py:355-379): relative change in percent of mean and population std
+      int stop = 0;
+      if (a.it > 0) {
+        const double m0 = st->prev_mean, s0 = st->prev_std;
+        const double cmn = (m0 == 0.0) ? ((mean == 0.0) ? 0.0 : kInf) : fabs((mean - m0) / m0 * 100.0);
+        const double csd = (s0 == 0.0) ? ((sd == 0.0) ? 0.0 : kInf) : fabs((sd - s0) / s0 * 100.0);
+        stop = (cmn < a.min_change && csd < a.min_change) ? 1 : 0;
+      }
+      st->prev_mean = mean;
+      st->prev_std = sd;
+      st->iterations_done = a.it + 1;
+      if (stop && a.arm_stop) st->stop = 1;
+      st->converged = stop;
+      wk.phase_t[9] = global_timer_ns();
     }
-    st->prev_mean = mean;
-    st->prev_std = sd;
-    st->iterations_done = a.it + 1;
-    if (stop && a.arm_stop) st->stop = 1;
-    st->converged = stop;
   }
 }
 
@@ -791,7 +1021,7 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
   const long long K = c.K;
   const bool multi = K > 4096;
   int G = 1;
-  if (multi) G = (int)std::min<long long>(c.num_sms, (K + RS_THREADS - 1) / RS_THREADS);
+  if (multi) G = (int)std::min<long long>(std::min(c.num_sms, 256), (K + RS_THREADS - 1) / RS_THREADS);
   // workspace: two parities
   const size_t hist_n = 2ull * RS_LEVELS * RS_BINS;
   if (c.ws.hist.cap < 2 * hist_n) {
@@ -843,6 +1073,8 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
   wk.minkey = c.ws.minkey.p + par * 2;
   wk.minkey_other = c.ws.minkey.p + (par ^ 1) * 2;
   wk.partials = c.ws.partials.p;
+  c.phase_t.reserve(32);
+  wk.phase_t = c.phase_t.p;
 
   if (multi) {
     void* args[] = {&a, &wk};
@@ -852,6 +1084,7 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
     k_reject_solve<false><<<1, RS_THREADS, 0, c.stream>>>(a, wk);
     SICP_CUDA(cudaGetLastError());
   }
+  c.tm.kernel_launches += 1;
 }
 
 void compact_residuals_launch(Ctx& c) {
@@ -864,6 +1097,7 @@ void compact_residuals_launch(Ctx& c) {
   k_compact_write<<<nb, 256, 0, c.stream>>>(c.keep.p, c.resid.p, K, c.compact_sums.p,
                                            c.resid_compact.p);
   SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 2;
 }
 
 }  // namespace sicp

@@ -59,6 +59,15 @@ struct RSWork {
   unsigned long long* minkey;
   unsigned long long* minkey_other;
   double* partials;
+  unsigned long long* phase_t;  // 32 x %globaltimer stamps of block 0 (diagnostics)
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
 
 }  // namespace sicp

@@ -44,6 +44,7 @@ void transform_launch(Ctx& c, const Rigid& T, const double* in, double* out, lon
       T, reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), n_pairs,
       in + 3 * (n - 1), out + 3 * (n - 1), has_tail);
   SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
 }
 
 }  // namespace sicp
