@@ -148,6 +148,9 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, n = args.correspondences, args.points
 
@@ -161,7 +164,7 @@ def run_b200(args):
 
     # ---- setup (untimed for `value`): resident inputs, grid, selection, normals
     eng.set_clouds(Xf_pin.numpy(), Xm_pin.numpy())
-    idx = np.unique(sb.pointcloud.subsample_indices(n, K)).astype(np.int64)
+    idx = sb.pointcloud.subsample_indices(n, K).astype(np.int64)
     eng.set_selected(idx)
     nrm = eng.estimate_normals(10)
     lsq = eng.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)

@@ -59,6 +59,7 @@ struct Ctx {
   double grid_target_occ = 3.0;
   int grid_max_rings = 8;
   int host_sync_every = 1;
+  int match_group = 0;   // lanes cooperating on one grid query: 0 = by K, else 1, 4, 8 or 16
 
   // clouds
   DevBuf<double> fix_xyz, mov_xyz;

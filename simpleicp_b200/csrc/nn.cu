@@ -117,6 +117,90 @@ __global__ void __launch_bounds__(128)
   out[i] = with_distance ? plane_distance(st->T, mov_xyz, bidx, px, py, pz, q_nrm[i]) : best;
 }
 
+// Cooperative variant: MG lanes share one query.  In ring 1 every lane owns one of the 9 grid
+// rows (x-contiguous cell triples), so the 9 dependent chains cell_start -> records run side by
+// side instead of back to back; the winners are combined with a shuffle min-reduction inside the
+// 16-lane group.  Later rings deal their (2r+1)^2 rows round-robin over the lanes.  The search is
+// latency-bound (a handful of 32-byte L2 sectors per query), so what counts is how many of
+// those loads are in flight — with one thread per query a K = 1000 search took 27 us.
+template <int MG>
+__global__ void __launch_bounds__(128)
+    k_match_grid_coop(GridView g, const DevState* __restrict__ st, const double* __restrict__ q_xyz,
+                      const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz,
+                      long long K, int rmax, int with_distance, long long* __restrict__ nn_idx,
+                      double* __restrict__ out, unsigned int* __restrict__ unresolved) {
+  const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long qi = gt / MG;
+  const int sub = threadIdx.x & (MG - 1);
+  if (qi >= K || st->stop) return;  // a whole group leaves together
+  const unsigned int gmask = (MG == 32) ? 0xffffffffu : (((1u << MG) - 1u) << ((threadIdx.x & 31) & ~(MG - 1)));
+  const Rigid Tinv = st->Tinv;
+  const double px = q_xyz[3 * qi + 0], py = q_xyz[3 * qi + 1], pz = q_xyz[3 * qi + 2];
+  double qx, qy, qz;
+  rigid_apply(Tinv, px, py, pz, qx, qy, qz);
+  const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+  const uint32_t* __restrict__ cs = g.cell_start;
+  double best = kInf;
+  long long bidx = -1;
+  bool resolved = false;
+  for (int r = 1;; ++r) {
+    const int x0 = cx - r, x1 = cx + r;
+    const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
+    const int side = 2 * r + 1, items = side * side;
+    for (int t = sub; t < items; t += MG) {
+      const int dz = t / side - r, dy = t % side - r;
+      const int y = cy + dy, z = cz + dz;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      const long long row = ((long long)z * g.ny + y) * g.nx;
+      const bool full = (r == 1) || dy == -r || dy == r || dz == -r || dz == r;
+      if (full) {
+        scan_range(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, best, bidx);
+      } else {
+        if (x0 >= 0) scan_range(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, best, bidx);
+        if (x1 < g.nx) scan_range(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, best, bidx);
+      }
+    }
+    // min-reduction of (d2, idx) over the 16 lanes of the group; every lane ends with the result
+#pragma unroll
+    for (int o = MG / 2; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(gmask, best, o, MG);
+      const long long oi = __shfl_xor_sync(gmask, bidx, o, MG);
+      if (od < best || (od == best && oi >= 0 && (bidx < 0 || oi < bidx))) {
+        best = od;
+        bidx = oi;
+      }
+    }
+    const int y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
+    double guard = kInf;
+    if (x0 > 0) guard = fmin(guard, qx - (g.ox + x0 * g.h));
+    if (x1 < g.nx - 1) guard = fmin(guard, (g.ox + (x1 + 1) * g.h) - qx);
+    if (y0 > 0) guard = fmin(guard, qy - (g.oy + y0 * g.h));
+    if (y1 < g.ny - 1) guard = fmin(guard, (g.oy + (y1 + 1) * g.h) - qy);
+    if (z0 > 0) guard = fmin(guard, qz - (g.oz + z0 * g.h));
+    if (z1 < g.nz - 1) guard = fmin(guard, (g.oz + (z1 + 1) * g.h) - qz);
+    if (guard >= kInf) {
+      resolved = true;
+      break;
+    }
+    guard -= 1e-9 * g.h;
+    if (guard > 0.0 && best <= guard * guard) {
+      resolved = true;
+      break;
+    }
+    if (r >= rmax) break;
+  }
+  if (sub != 0) return;
+  if (!resolved) {
+    const unsigned int slot = atomicAdd(&unresolved[K], 1u);
+    unresolved[slot] = (unsigned int)qi;
+    return;
+  }
+  nn_idx[qi] = bidx;
+  out[qi] = with_distance ? plane_distance(st->T, mov_xyz, bidx, px, py, pz, q_nrm[qi]) : best;
+}
+
 // ------------------------------------------------------------------------------------------
 // brute-force engine (TMA staged)
 // ------------------------------------------------------------------------------------------
@@ -438,9 +522,27 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   SICP_CUDA(cudaMemsetAsync(c.unresolved.p + K, 0, sizeof(unsigned int), c.stream));
   const bool use_bf = (c.nn_engine == SICP_NN_AUTO) && allow_bf;
   const int rmax = use_bf ? c.grid_max_rings : (1 << 30);
-  k_match_grid<<<(unsigned)((K + 127) / 128), 128, 0, c.stream>>>(
-      c.gmov.view(), c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p, K, rmax, with_distance ? 1 : 0,
-      c.nn_idx.p, out, c.unresolved.p);
+  if (c.match_group == 1) {
+    k_match_grid<<<(unsigned)((K + 127) / 128), 128, 0, c.stream>>>(
+        c.gmov.view(), c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p, K, rmax,
+        with_distance ? 1 : 0, c.nn_idx.p, out, c.unresolved.p);
+  } else {
+    // lanes per query: 16 while the search is latency-bound (few queries), fewer once there are
+    // enough queries to fill the machine and issue slots become the limit
+    int mg = c.match_group;
+    if (mg == 0) mg = (K <= 16384) ? 16 : ((K <= 65536) ? 8 : 4);
+    const long long threads = K * mg;
+    const unsigned blocks = (unsigned)((threads + 127) / 128);
+#define SICP_LAUNCH_COOP(N)                                                                  \
+  k_match_grid_coop<N><<<blocks, 128, 0, c.stream>>>(c.gmov.view(), c.dev_state.p, c.q_xyz.p, \
+                                                    c.q_nrm.p, c.mov_xyz.p, K, rmax,          \
+                                                    with_distance ? 1 : 0, c.nn_idx.p, out,   \
+                                                    c.unresolved.p)
+    if (mg == 4) SICP_LAUNCH_COOP(4);
+    else if (mg == 8) SICP_LAUNCH_COOP(8);
+    else SICP_LAUNCH_COOP(16);
+#undef SICP_LAUNCH_COOP
+  }
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 1;
   if (mid) SICP_CUDA(cudaEventRecord(mid, c.stream));

@@ -69,6 +69,7 @@ struct Shared {
   double gk[6];
   double delta[6];
   int spd;
+  unsigned long long stamp[2];
   // in-block refinement of the selected radix bin
   unsigned int h256[256];
   unsigned long long small[64];
@@ -517,8 +518,9 @@ __device__ void lm_solve(Shared& s, const RSArgs& a, double w, const double* x0,
   };
   lm_eval(s, x, cm, cf, lane);
   keep_eval();
+  if (lane == 0) s.stamp[0] = global_timer_ns();
   double F = w2 * s.F + obs_cost(x);
-  double lambda = 0.0;
+  double lambda = 0.0, rel_prev = 0.0;
   int it = 0, ok = 1;
   for (it = 0; it < 40 && nf > 0; ++it) {
     if (lane == 0) {
@@ -541,6 +543,7 @@ __device__ void lm_solve(Shared& s, const RSArgs& a, double w, const double* x0,
 #pragma unroll
       for (int i = 0; i < 6; ++i) s.delta[i] = br[i];
       s.spd = spd ? 1 : 0;
+      if (it == 0) s.stamp[1] = global_timer_ns();
     }
     __syncwarp();
     if (!s.spd) {
@@ -560,9 +563,15 @@ __device__ void lm_solve(Shared& s, const RSArgs& a, double w, const double* x0,
       rel = fmax(rel, fabs(dj) / fmax(fabs(x[j]), 1e-3));
     }
     __syncwarp();
-    if (rel < 1e-9 && lambda == 0.0) {
-      // undamped Gauss-Newton step below 1e-9 relative: converged; take it without another
-      // evaluation (the reference's own solver stops at ftol = xtol = 1e-8)
+    // Gauss-Newton contracts linearly with a rate rho << 1 on these small-residual problems;
+    // rho is estimated from consecutive steps (prior 1e-2 for the first one).  Once the error
+    // predicted to remain AFTER taking this step, rel * rho / (1 - rho), is below 3e-10 the step
+    // is taken and the loop ends without another evaluation (the reference's own solver stops
+    // at ftol = xtol = 1e-8).
+    const double rho = (rel_prev > 0.0) ? fmin(fmax(rel / rel_prev, 1e-6), 0.5) : 1e-2;
+    const double remaining = rel * rho / (1.0 - rho);
+    rel_prev = rel;
+    if ((rel < 1e-9 || remaining < 3e-10) && lambda == 0.0) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) x[j] = xn[j];
       ++it;
@@ -794,6 +803,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
         for (int u = 0; u < NB; ++u) v += r[q][u];
         v = warp_sum(v);
         if (lane == 0 && o < RS_NPART) s.tot[o] = v;
+        if (q == 0) RS_STAMP(20);
       }
     }
     __syncthreads();
@@ -835,7 +845,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       lo.ok = 1;
       if (!skip) {
         lm_solve(s, a, w, st->x, cm, cf, lo, lane);
-        if (lane == 0) wk.phase_t[19] = global_timer_ns();
+        if (lane == 0) {
+          wk.phase_t[19] = global_timer_ns();
+          wk.phase_t[21] = s.stamp[0];
+          wk.phase_t[22] = s.stamp[1];
+        }
       }
       if (lane == 0) {
         rec->n_kept = n_kept;

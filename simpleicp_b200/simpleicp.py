@@ -145,8 +145,10 @@ def register(
         _log.info("Select points for correspondences in fixed point cloud ...")
         m = n_fix if idx is None else idx.size
         if m > correspondences:
+            # rint(linspace(0, m-1, n)) with m > n has a step > 1, so the picks are strictly
+            # increasing: already the sorted, duplicate-free index set the reference ends up with
             pick = pointcloud.subsample_indices(m, correspondences)
-            idx = np.unique(pick if idx is None else idx[pick]).astype(np.int64)
+            idx = (pick if idx is None else idx[pick]).astype(np.int64)
         eng.set_selected(idx)
         if idx is None:
             idx = np.arange(n_fix, dtype=np.int64)

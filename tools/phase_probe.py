@@ -18,7 +18,7 @@ def probe(n, K, rings=(4, 8, 12, 16)):
     X_fix, X_mov, _ = make_pair(n, 0)
     with _capi.Engine() as e:
         e.set_clouds(X_fix, X_mov)
-        idx = np.unique(sb.pointcloud.subsample_indices(n, K)).astype(np.int64)
+        idx = sb.pointcloud.subsample_indices(n, K).astype(np.int64)
         e.set_selected(idx)
         e.estimate_normals(10)
         lsq = e.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
@@ -43,10 +43,28 @@ def probe(n, K, rings=(4, 8, 12, 16)):
             seq = " ".join(f"{LABELS[i]}={t[i]:.1f}" for i in range(1, 10))
             sel = (f"med[lv={t[24]:.0f} cand={t[26]:.0f}: levels={t[10]:.1f} gather={t[11]:.1f} sort={t[12]:.1f}] "
                    f"mad[lv={t[25]:.0f} cand={t[27]:.0f}: levels={t[14]:.1f} gather={t[15]:.1f} sort={t[16]:.1f}]")
-            print("  phases(us): " + seq + f" | D: reduce={t[17]:.1f} assemble={t[18]:.1f} lm={t[19]:.1f} lm_it={rec_lm}")
+            print("  phases(us): " + seq + f" | D: red1={t[20]:.1f} reduce={t[17]:.1f} assemble={t[18]:.1f} eval0={t[21]:.1f} chol0={t[22]:.1f} lm={t[19]:.1f} lm_it={rec_lm}")
             print("  " + sel)
-        st = e.time_stages(p, 10, False)
-        print("  stages warm (ms):", {k: round(v, 4) for k, v in st.items()})
+        for mg in (1, 4, 8, 16):
+            e.set_option("match_group", mg)
+            sw = e.time_stages(p, 10, False)
+            sc = e.time_stages(p, 10, True)
+            print(f"  match_group={mg:2d}: match warm {sw['match_grid']*1e3:6.1f} us  cold {sc['match_grid']*1e3:6.1f} us")
+        e.set_option("match_group", 0)
+    for occ in (1.5, 2.0, 4.0, 6.0):
+        with _capi.Engine() as e:
+            e.set_option("grid_target_occupancy", occ)
+            e.set_clouds(X_fix, X_mov)
+            e.set_selected(idx)
+            e.estimate_normals(10)
+            lsq = e.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
+            p = e.run_params(0.3, 1.0, 100, lsq)
+            e.iterate(p, x_in=np.zeros(6), want_record=True)
+            for _ in range(4):
+                e.iterate(p, want_record=True)
+            sw = e.time_stages(p, 10, False)
+            tm = e.timings()
+            print(f"  occupancy target {occ}: match warm {sw['match_grid']*1e3:6.1f} us, grid build {tm['grid_mov_ms']:.3f} ms, normals {tm['normals_ms']:.3f} ms")
 
 
 if __name__ == "__main__":
