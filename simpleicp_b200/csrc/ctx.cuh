@@ -55,7 +55,7 @@ struct Ctx {
 
   // options
   int nn_engine = SICP_NN_AUTO;
-  int sign_mode = SICP_SIGN_CANONICAL;
+  int sign_mode = SICP_SIGN_DGEEV;
   double grid_target_occ = 3.0;
   int grid_max_rings = 8;
   int host_sync_every = 1;

@@ -243,6 +243,47 @@ def test_full_run_with_reference_normals(gpu, name):
     np.testing.assert_allclose(np.asarray(res.X_mov_transformed)[:64], g["X_mov_t_head"], rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("name,k", [("dragon", 10), ("bunny", 10), ("webots", 40), ("multisensor", 10)])
+def test_normal_signs_follow_numpy_eig(gpu, name, k):
+    """Default sign mode: the kernel walks LAPACK dgeev's algorithm, so eigenvector signs (and
+    with them the float32 normals) equal the reference's np.linalg.eig output; the few
+    exceptions are rounding-borderline deflations (DESIGN.md "normal sign")."""
+    g = load_golden(name)
+    X_fix, X_mov = load_pair(name)
+    with _capi.Engine() as e:
+        e.set_clouds(X_fix, X_mov)
+        e.set_selected(g["idx_sel"])
+        nx, ny, nz, pl = e.estimate_normals(k)
+    n_gpu = np.column_stack((nx, ny, nz))
+    ok = np.isfinite(g["planarity"]) & (g["planarity"] > 0.05)
+    same_sign = np.sum(n_gpu.astype(np.float64) * g["normals"].astype(np.float64), axis=1) > 0
+    frac = same_sign[ok].mean()
+    exact = (n_gpu[ok] == g["normals"][ok]).all(axis=1).mean()
+    print(f"{name}: sign agreement {frac:.4f}, bit-identical float32 normals {exact:.4f}")
+    assert frac > 0.985
+    # webots (k = 40 on a regular lattice) has equal-distance ties at the 40th neighbour in ~28 %
+    # of its neighbourhoods; cKDTree's tie order is unspecified, ours is lowest index
+    assert exact > (0.8 if name == "webots" else 0.98)
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_full_run_standalone(gpu, name):
+    """Everything on the GPU, normals included (dgeev-sign mode): H against the reference's."""
+    g = load_golden(name)
+    X_fix, X_mov = load_pair(name)
+    res = sb.register(X_fix, X_mov, **g["kwargs"])
+    dH = np.linalg.norm(res.H - g["H"])
+    print(f"{name} stand-alone: |dH|_F = {dH:.3e}, iterations {res.iterations} vs {g['it_x'].shape[0]}")
+    # dragon (graded: 1e-5), dragon_observed and bunny reproduce the reference far below its own
+    # solver tolerance.  webots / multisensor inherit inputs on which the reference itself is not
+    # uniquely defined (k-th-neighbour ties on a lattice; a 316-point radar cloud whose stop rule
+    # flips on single correspondences): a handful of differing normals moves H at the 1e-3..1e-2
+    # level there — with the reference's normals injected both reproduce it to 3e-10
+    # (test_full_run_with_reference_normals).
+    tol = {"dragon": 1e-9, "dragon_observed": 1e-8, "bunny": 1e-5, "webots": 1e-2, "multisensor": 5e-2}[name]
+    assert dH < tol
+
+
 def test_dragon_end_to_end_graded(gpu):
     """BASELINE.json north star: H within 1e-5 Frobenius of the Python reference on data/dragon,
     everything (normals included) computed on the GPU."""
@@ -299,7 +340,7 @@ def test_facade_side_effects(gpu):
     np.testing.assert_allclose(rbp.H, H, rtol=0, atol=1e-15)
     assert len(res) > 6
     g = load_golden("bunny")
-    assert np.linalg.norm(H - g["H"]) < 2e-3  # canonical normal sign: different kept sets
+    assert np.linalg.norm(H - g["H"]) < 1e-4
     # second run reuses the stored normal columns (reference hook simpleicp.py:176-178)
     pc_mov2 = sb.PointCloud(X_mov, columns=["x", "y", "z"], copy=True)
     pc_fix.select_all_points()
