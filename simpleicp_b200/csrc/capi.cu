@@ -236,6 +236,9 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
   } else if (k == "grid_max_rings") {
     SICP_REQUIRE(value >= 1 && value <= 1e6, SICP_ERR_BAD_ARG, "grid_max_rings out of range");
     c.grid_max_rings = (int)value;
+  } else if (k == "rs_blocks") {
+    SICP_REQUIRE(value >= 0 && value <= 256, SICP_ERR_BAD_ARG, "rs_blocks out of range");
+    c.rs_blocks = (int)value;
   } else if (k == "match_group") {
     SICP_REQUIRE(value == 0 || value == 1 || value == 4 || value == 8 || value == 16, SICP_ERR_BAD_ARG,
                  "match_group must be 0 (auto), 1, 4, 8 or 16");

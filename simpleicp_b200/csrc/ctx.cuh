@@ -59,6 +59,7 @@ struct Ctx {
   double grid_target_occ = 3.0;
   int grid_max_rings = 8;
   int host_sync_every = 1;
+  int rs_blocks = 0;     // blocks of the cooperative reject/solve kernel (0 = one per SM)
   int match_group = 0;   // lanes cooperating on one grid query: 0 = by K, else 1, 4, 8 or 16
 
   // clouds
@@ -105,6 +106,7 @@ struct Ctx {
   DevBuf<unsigned int> misc_counters;     // grid build / API scratch counters
   DevBuf<unsigned char> flush_buf;        // 256 MiB scratch for cold-L2 measurements
   DevBuf<unsigned long long> phase_t;     // %globaltimer stamps of the reject/solve kernel
+  DevBuf<unsigned int> grid_bar;          // grid barrier of the cooperative reject/solve kernel
   sicp_iter_record* rec_host = nullptr;  // pinned
   double* scal_host = nullptr;           // pinned staging for small reads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

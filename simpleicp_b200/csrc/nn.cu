@@ -27,17 +27,32 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // grid engine
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void consider(const Rec& r, double qx, double qy, double qz,
+                                         double& best, long long& bidx) {
+  const double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
+  const double d2 = dx * dx + dy * dy + dz * dz;
+  if (d2 < best || (d2 == best && r.idx < bidx)) {
+    best = d2;
+    bidx = r.idx;
+  }
+}
+
+// Scan the records [s, e).  The search is latency-bound, so four 32-byte records (LDG.E.256
+// each) are requested before the first one is used; the tail re-reads the last record instead
+// of branching (a duplicate never changes the result: same distance, same index).
 __device__ __forceinline__ void scan_range(const Rec* __restrict__ recs, uint32_t s, uint32_t e,
                                            double qx, double qy, double qz, double& best,
                                            long long& bidx) {
-  for (uint32_t i = s; i < e; ++i) {
-    const Rec r = recs[i];  // one LDG.E.256
-    const double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
-    const double d2 = dx * dx + dy * dy + dz * dz;
-    if (d2 < best || (d2 == best && r.idx < bidx)) {
-      best = d2;
-      bidx = r.idx;
-    }
+  for (uint32_t i = s; i < e; i += 4) {
+    const uint32_t last = e - 1;
+    const Rec r0 = recs[i];
+    const Rec r1 = recs[min(i + 1, last)];
+    const Rec r2 = recs[min(i + 2, last)];
+    const Rec r3 = recs[min(i + 3, last)];
+    consider(r0, qx, qy, qz, best, bidx);
+    consider(r1, qx, qy, qz, best, bidx);
+    consider(r2, qx, qy, qz, best, bidx);
+    consider(r3, qx, qy, qz, best, bidx);
   }
 }
 
@@ -148,18 +163,70 @@ __global__ void __launch_bounds__(128)
   for (int r = 1;; ++r) {
     const int x0 = cx - r, x1 = cx + r;
     const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
-    const int side = 2 * r + 1, items = side * side;
-    for (int t = sub; t < items; t += MG) {
-      const int dz = t / side - r, dy = t % side - r;
-      const int y = cy + dy, z = cz + dz;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      const long long row = ((long long)z * g.ny + y) * g.nx;
-      const bool full = (r == 1) || dy == -r || dy == r || dz == -r || dz == r;
-      if (full) {
-        scan_range(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, best, bidx);
-      } else {
-        if (x0 >= 0) scan_range(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, best, bidx);
-        if (x1 < g.nx) scan_range(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, best, bidx);
+    if (r == 1) {
+      // Ring 1 in two steps.  (1) the query's own x-row, one cell per lane; (2) the eight
+      // neighbouring rows, each skipped (or narrowed in x) when the distance from the query to
+      // the row / cell already exceeds the best distance of step 1 — the nearest neighbour
+      // is usually in the own row, so most of the 27 cells are never read.
+      if (sub < 3) {
+        const int x = cx - 1 + sub;
+        if (x >= 0 && x < g.nx) {
+          const long long row0 = ((long long)cz * g.ny + cy) * g.nx;
+          scan_range(g.recs, cs[row0 + x], cs[row0 + x + 1], qx, qy, qz, best, bidx);
+        }
+      }
+#pragma unroll
+      for (int o = MG / 2; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(gmask, best, o, MG);
+        const long long oi = __shfl_xor_sync(gmask, bidx, o, MG);
+        if (od < best || (od == best && oi >= 0 && (bidx < 0 || oi < bidx))) {
+          best = od;
+          bidx = oi;
+        }
+      }
+      // distances from the query to the faces of its own cell (>= 0 up to rounding)
+      const double fxl = fmax(qx - (g.ox + cx * g.h), 0.0), fxh = fmax((g.ox + (cx + 1) * g.h) - qx, 0.0);
+      const double fyl = fmax(qy - (g.oy + cy * g.h), 0.0), fyh = fmax((g.oy + (cy + 1) * g.h) - qy, 0.0);
+      const double fzl = fmax(qz - (g.oz + cz * g.h), 0.0), fzh = fmax((g.oz + (cz + 1) * g.h) - qz, 0.0);
+      const double lim = best * (1.0 + 1e-12);  // strictly farther only: ties are still visited
+      constexpr int NR = (8 + MG - 1) / MG;  // rows per lane in step 2
+      uint32_t rs[NR], re[NR];
+#pragma unroll
+      for (int u = 0; u < NR; ++u) {
+        rs[u] = re[u] = 0;
+        const int t = sub + u * MG;
+        if (t >= 8) continue;
+        const int tt = t + (t >= 4 ? 1 : 0);  // 0..8 without the centre (4)
+        const int dz = tt / 3 - 1, dy = tt % 3 - 1;
+        const int y = cy + dy, z = cz + dz;
+        if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+        const double by = (dy < 0) ? fyl : ((dy > 0) ? fyh : 0.0);
+        const double bz = (dz < 0) ? fzl : ((dz > 0) ? fzh : 0.0);
+        const double lb = by * by + bz * bz;
+        if (lb > lim) continue;
+        int xs = xa, xe = xb;
+        if (x0 >= 0 && lb + fxl * fxl > lim) xs = cx;
+        if (x1 < g.nx && lb + fxh * fxh > lim) xe = cx;
+        const long long row = ((long long)z * g.ny + y) * g.nx;
+        rs[u] = cs[row + xs];
+        re[u] = cs[row + xe + 1];
+      }
+#pragma unroll
+      for (int u = 0; u < NR; ++u) scan_range(g.recs, rs[u], re[u], qx, qy, qz, best, bidx);
+    } else {
+      const int side = 2 * r + 1, items = side * side;
+      for (int t = sub; t < items; t += MG) {
+        const int dz = t / side - r, dy = t % side - r;
+        const int y = cy + dy, z = cz + dz;
+        if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+        const long long row = ((long long)z * g.ny + y) * g.nx;
+        const bool full = dy == -r || dy == r || dz == -r || dz == r;
+        if (full) {
+          scan_range(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, best, bidx);
+        } else {
+          if (x0 >= 0) scan_range(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, best, bidx);
+          if (x1 < g.nx) scan_range(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, best, bidx);
+        }
       }
     }
     // min-reduction of (d2, idx) over the 16 lanes of the group; every lane ends with the result

@@ -77,10 +77,38 @@ struct Shared {
   unsigned int small_n;
 };
 
+// Grid-wide barrier for the cooperative launch (all blocks co-resident).  Hand-written instead of
+// cooperative_groups' grid.sync() so that waiting blocks BACK OFF (__nanosleep): while block 0
+// runs its serial phases the other 147 blocks would otherwise hammer one L2 line with polling
+// loads and slow exactly the block everybody is waiting for.  bar[0] = arrival count,
+// bar[1] = generation.  The fence after the wait also invalidates this SM's L1 (gpu-scope
+// fence), so data written by other blocks before the barrier is re-read from L2.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int gen = *(volatile unsigned int*)(bar + 1);
+    const unsigned int old = atomicAdd(bar, 1u);
+    if (old == nblocks - 1u) {
+      *(volatile unsigned int*)bar = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      unsigned int ns = 32;
+      while (*(volatile unsigned int*)(bar + 1) == gen) {
+        __nanosleep(ns);
+        if (ns < 256) ns *= 2;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 template <bool MULTI>
-__device__ __forceinline__ void gsync() {
+__device__ __forceinline__ void gsync(unsigned int* bar) {
   if (MULTI)
-    cg::this_grid().sync();
+    grid_barrier(bar, gridDim.x);
   else
     __syncthreads();
 }
@@ -266,7 +294,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     if (MULTI) {
       for (int b = threadIdx.x; b < n_bins; b += RS_THREADS)
         if (s.hist[b]) atomicAdd(&gh[b], s.hist[b]);
-      gsync<MULTI>();
+      gsync<MULTI>(wk.barrier);
     }
     const unsigned int* src = MULTI ? gh : s.hist;
     unsigned int total = 0;
@@ -336,7 +364,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
       wmin[0] = m;
     }
   }
-  gsync<MULTI>();
+  gsync<MULTI>(wk.barrier);
   if (blockIdx.x == 0 && threadIdx.x == 0) wk.phase_t[11 + SEL * 4] = global_timer_ns();
   const unsigned long long above = MULTI ? *gmin : wmin[0];
   unsigned long long klo, khi;
@@ -773,7 +801,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     }
   }
   RS_STAMP(3);
-  gsync<MULTI>();
+  gsync<MULTI>(wk.barrier);
   RS_STAMP(4);
 
   // ---- D: block 0 reduces the partials and solves
@@ -874,7 +902,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     }
   }
   RS_STAMP(5);
-  gsync<MULTI>();
+  gsync<MULTI>(wk.barrier);
   RS_STAMP(6);
   if (st->skip) return;
 
@@ -918,7 +946,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     }
   }
   RS_STAMP(7);
-  gsync<MULTI>();
+  gsync<MULTI>(wk.barrier);
   RS_STAMP(8);
   if (blockIdx.x == 0 && warp == 0) {
     double t0 = 0, t1 = 0;
@@ -1035,7 +1063,10 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
   const long long K = c.K;
   const bool multi = K > 4096;
   int G = 1;
-  if (multi) G = (int)std::min<long long>(std::min(c.num_sms, 256), (K + RS_THREADS - 1) / RS_THREADS);
+  if (multi) {
+    const int cap = (c.rs_blocks > 0) ? std::min(c.rs_blocks, c.num_sms) : std::min(c.num_sms, 256);
+    G = (int)std::min<long long>(cap, (K + RS_THREADS - 1) / RS_THREADS);
+  }
   // workspace: two parities
   const size_t hist_n = 2ull * RS_LEVELS * RS_BINS;
   if (c.ws.hist.cap < 2 * hist_n) {
@@ -1089,6 +1120,11 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
   wk.partials = c.ws.partials.p;
   c.phase_t.reserve(32);
   wk.phase_t = c.phase_t.p;
+  if (c.grid_bar.p == nullptr) {
+    c.grid_bar.reserve(2);
+    SICP_CUDA(cudaMemsetAsync(c.grid_bar.p, 0, 2 * sizeof(unsigned int), c.stream));
+  }
+  wk.barrier = c.grid_bar.p;
 
   if (multi) {
     void* args[] = {&a, &wk};

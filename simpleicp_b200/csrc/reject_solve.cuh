@@ -60,6 +60,7 @@ struct RSWork {
   unsigned long long* minkey_other;
   double* partials;
   unsigned long long* phase_t;  // 32 x %globaltimer stamps of block 0 (diagnostics)
+  unsigned int* barrier;        // {arrival count, generation} of the grid barrier
 };
 
 #ifdef __CUDACC__
