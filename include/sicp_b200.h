@@ -190,6 +190,19 @@ int32_t sicp_time_stages(sicp_ctx* ctx, const sicp_run_params* p, int32_t reps, 
  * [24],[25] radix levels used, [26],[27] candidates sorted (raw counts, not times).            */
 int32_t sicp_get_phase_times(sicp_ctx* ctx, double us[32] /*[h]*/);
 
+/* ---- .xyz text I/O (host only; SURVEY.md section 8f: file parsing dominates end-to-end time on
+ * the lidar sets).  Contract of the reference readers (c++/src/simpleicp-cli.cpp:72-128,
+ * rust/src/io.rs:9-37, np.genfromtxt in python/simpleicp/tests/test_simpleicp.py:102-103):
+ * whitespace-separated x y z per line; '/' or '#' comment lines and blank lines are skipped.
+ * sicp_xyz_load allocates *xyz (n x 3 float64, row-major); release it with sicp_xyz_free.
+ * sicp_xyz_save mirrors PointCloud.write_xyz (python/simpleicp/pointcloud.py:219-226):
+ * header != 0 writes the "//X Y Z" line, decimals < 0 writes round-trip precision.            */
+int32_t sicp_xyz_load(const char* path, double** xyz /*out*/, int64_t* n /*out*/);
+void sicp_xyz_free(double* xyz);
+int32_t sicp_xyz_save(const char* path, const double* xyz /*[h] n x 3*/, int64_t n,
+                      int32_t decimals, int32_t header);
+const char* sicp_io_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,9 +13,10 @@ _logging.getLogger(__name__).addHandler(_logging.NullHandler())
 from .simpleicp import SimpleICP, SimpleICPException, simpleicp, register  # noqa: E402
 from .pointcloud import PointCloud, PointCloudException  # noqa: E402
 from .optimization import RigidBodyParameters, Parameter  # noqa: E402
-from .batch import simpleicp_batch, shard_pairs  # noqa: E402
+from .batch import simpleicp_batch, shard_pairs, tile_slabs  # noqa: E402
+from ._capi import read_xyz, write_xyz  # noqa: E402
 
 __all__ = [
     "SimpleICP", "SimpleICPException", "PointCloud", "PointCloudException", "RigidBodyParameters",
-    "Parameter", "simpleicp", "register", "simpleicp_batch", "shard_pairs",
+    "Parameter", "simpleicp", "register", "simpleicp_batch", "shard_pairs", "tile_slabs", "read_xyz", "write_xyz",
 ]

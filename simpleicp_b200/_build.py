@@ -20,7 +20,9 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "libsicp_b200.so"
-SOURCES = ["capi.cu", "grid.cu", "nn.cu", "normals.cu", "reject_solve.cu", "transform.cu"]
+SOURCES = ["capi.cu", "grid.cu", "nn.cu", "normals.cu", "reject_solve.cu", "transform.cu", "io.cpp"]
+CLI_SRC = PKG.parent / "cli" / "sicp_cli.cpp"
+CLI_BIN = PKG / "sicp_cli"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "-Xptxas", "-v"]
@@ -35,7 +37,8 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "sicp_b200.h"]):
+    for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) +
+                    [PKG.parent / "include" / "sicp_b200.h", CLI_SRC]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
     h.update(" ".join(ARCH + FLAGS).encode())
@@ -51,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
 
     def compile_one(src: str):
-        obj = OBJ / (src[:-3] + ".o")
+        obj = OBJ / (src.rsplit(".", 1)[0] + ".o")
         cmd = [nvcc, *ARCH, *FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
@@ -62,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             if r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
                 raise RuntimeError(f"nvcc failed on {src}")
-            (OBJ / (src[:-3] + ".ptxas.txt")).write_text(r.stderr)
+            (OBJ / (src.rsplit(".", 1)[0] + ".ptxas.txt")).write_text(r.stderr)
             if verbose:
                 sys.stderr.write(r.stderr)
             objs.append(str(obj))
@@ -71,6 +74,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    # command-line front end with the reference CLI's flag set (c++/src/simpleicp-cli.cpp:15-35)
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I", str(PKG.parent / "include"), str(CLI_SRC), "-o", str(CLI_BIN),
+           "-L", str(PKG), "-lsicp_b200", "-Wl,-rpath,$ORIGIN", "-lpthread", "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building sicp_cli failed")
     stamp.write_text(dig)
     return LIB
 

@@ -27,6 +27,7 @@ SYMBOLS = (
     "sicp_set_normals", "sicp_get_knn", "sicp_match", "sicp_reject", "sicp_solve",
     "sicp_uncertainties", "sicp_run", "sicp_get_residuals", "sicp_iterate", "sicp_transform",
     "sicp_get_timings", "sicp_time_stages", "sicp_get_phase_times",
+    "sicp_xyz_load", "sicp_xyz_free", "sicp_xyz_save", "sicp_io_last_error",
 )
 
 
@@ -112,8 +113,41 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = i32
+    lib.sicp_xyz_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(dbl)), C.POINTER(i64)]
+    lib.sicp_xyz_load.restype = i32
+    lib.sicp_xyz_free.argtypes = [C.POINTER(dbl)]
+    lib.sicp_xyz_free.restype = None
+    lib.sicp_xyz_save.argtypes = [C.c_char_p, vp, i64, i32, i32]
+    lib.sicp_xyz_save.restype = i32
+    lib.sicp_io_last_error.restype = C.c_char_p
     _lib = lib
     return lib
+
+
+def read_xyz(path) -> np.ndarray:
+    """Fast multi-threaded .xyz reader (x y z per line, '/'/'#' comment lines skipped); the
+    doubles equal what np.genfromtxt parses from the same text."""
+    lib = load_library()
+    p = C.POINTER(C.c_double)()
+    n = C.c_int64(0)
+    rc = lib.sicp_xyz_load(str(path).encode(), C.byref(p), C.byref(n))
+    if rc != SICP_OK:
+        raise OSError(lib.sicp_io_last_error().decode())
+    try:
+        return np.ctypeslib.as_array(p, shape=(int(n.value), 3)).copy()
+    finally:
+        lib.sicp_xyz_free(p)
+
+
+def write_xyz(path, X, decimals: int = 3, header: bool = True) -> None:
+    """CloudCompare-style text file like the reference's PointCloud.write_xyz."""
+    lib = load_library()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    if X.ndim != 2 or X.shape[1] != 3:
+        raise ValueError("X must have 3 columns!")
+    rc = lib.sicp_xyz_save(str(path).encode(), X.ctypes.data, X.shape[0], int(decimals), int(header))
+    if rc != SICP_OK:
+        raise OSError(lib.sicp_io_last_error().decode())
 
 
 def _ptr(a) -> Optional[int]:

@@ -52,6 +52,24 @@ def gather_records(local: np.ndarray, n_pairs: int, world_size: int, rank: int, 
     return out
 
 
+def tile_slabs(X_fix: np.ndarray, X_mov: np.ndarray, n_slabs: int, overlap: float, axis: int = 0):
+    """Cut a large pair into `n_slabs` overlapping slabs along `axis` (BASELINE.json configs[3],
+    SURVEY.md section 8d C4): equal-count quantile cuts of the fixed cloud's coordinate, the same
+    cuts for both clouds, every slab widened by `overlap` on both sides.  Each slab is an
+    independent registration.  Returns a list of (X_fix_slab, X_mov_slab)."""
+    if n_slabs < 1:
+        raise ValueError("n_slabs must be >= 1")
+    cuts = np.quantile(X_fix[:, axis], np.linspace(0.0, 1.0, n_slabs + 1))
+    cuts[0], cuts[-1] = -np.inf, np.inf
+    out = []
+    for s in range(n_slabs):
+        lo, hi = cuts[s] - overlap, cuts[s + 1] + overlap
+        mf = (X_fix[:, axis] >= lo) & (X_fix[:, axis] < hi)
+        mm = (X_mov[:, axis] >= lo) & (X_mov[:, axis] < hi)
+        out.append((np.ascontiguousarray(X_fix[mf]), np.ascontiguousarray(X_mov[mm])))
+    return out
+
+
 def simpleicp_batch(
     pairs: Sequence[Tuple[np.ndarray, np.ndarray]] | Callable[[int], Tuple[np.ndarray, np.ndarray]],
     n_pairs: Optional[int] = None,
@@ -61,6 +79,7 @@ def simpleicp_batch(
     dist=None,
     device: int = 0,
     register_fn=None,
+    concurrency: int = 4,
     **run_kwargs,
 ) -> np.ndarray:
     """Register every pair; returns the (n_pairs, 20) record table on every rank.
@@ -68,33 +87,56 @@ def simpleicp_batch(
     `pairs` is a sequence or a generator function i -> (X_fix, X_mov) (so that ranks only
     materialise their own share).  `register_fn` defaults to the GPU pipeline
     (simpleicp_b200.register on cuda:`device`); tests inject a stub to exercise the sharding and
-    the collective on CPU.
+    the collective on CPU.  On the GPU path `concurrency` engines, each on its own CUDA stream and
+    driven by its own thread (the C calls release the GIL), work through the rank's share so the
+    host round trips of small registrations overlap.
     """
     if n_pairs is None:
         n_pairs = len(pairs)  # type: ignore[arg-type]
     get = pairs if callable(pairs) else (lambda i: pairs[i])  # type: ignore[index]
     mine = shard_pairs(n_pairs, world_size, rank)
-    eng = None
-    if register_fn is None:
+    local = np.zeros((len(mine), RECORD_LEN))
+
+    def record(res):
+        last = res.records[res.iterations - 1]
+        return pack_record(res.H, res.iterations, last["n_kept"], last["mean_res"], last["std_res"])
+
+    if register_fn is not None:
+        for j, i in enumerate(mine):
+            Xf, Xm = get(i)
+            local[j] = record(register_fn(Xf, Xm, **run_kwargs))
+    else:
+        import threading
+
+        import torch
+
         from . import _capi
         from .simpleicp import register
 
-        eng = _capi.Engine(device)
+        n_workers = max(1, min(concurrency, len(mine)))
+        errors = []
 
-        def register_fn(Xf, Xm, **kw):  # noqa: E306
-            return register(Xf, Xm, engine=eng, **kw)
+        def worker(w):
+            try:
+                with torch.cuda.device(device):
+                    stream = torch.cuda.Stream(device=device)
+                    eng = _capi.Engine(device, stream=int(stream.cuda_stream))
+                    try:
+                        for j in range(w, len(mine), n_workers):
+                            Xf, Xm = get(mine[j])
+                            local[j] = record(register(Xf, Xm, engine=eng, **run_kwargs))
+                    finally:
+                        eng.close()
+            except Exception as e:  # surfaced after the join
+                errors.append(e)
 
-    local = np.zeros((len(mine), RECORD_LEN))
-    try:
-        for j, i in enumerate(mine):
-            Xf, Xm = get(i)
-            res = register_fn(Xf, Xm, **run_kwargs)
-            last = res.records[res.iterations - 1]
-            local[j] = pack_record(res.H, res.iterations, last["n_kept"], last["mean_res"],
-                                   last["std_res"])
-    finally:
-        if eng is not None:
-            eng.close()
+        threads = [threading.Thread(target=worker, args=(w,)) for w in range(n_workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
     dev = None
     if dist is not None and world_size > 1:
         import torch

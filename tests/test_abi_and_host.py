@@ -164,6 +164,23 @@ def test_shard_pairs_partition():
     assert batch.shard_pairs(10, 4, 1) == [1, 5, 9]
 
 
+def test_tile_slabs():
+    rng = np.random.default_rng(0)
+    Xf = rng.uniform(0, 100, size=(5000, 3))
+    Xm = rng.uniform(0, 100, size=(4000, 3))
+    slabs = batch.tile_slabs(Xf, Xm, 4, overlap=2.5)
+    assert len(slabs) == 4
+    cuts = np.quantile(Xf[:, 0], [0.25, 0.5, 0.75])
+    # every fixed point is in at least one slab, interior points near a cut are in two
+    total = sum(len(a) for a, _ in slabs)
+    assert total > len(Xf)
+    for s, (a, b) in enumerate(slabs):
+        lo = -np.inf if s == 0 else cuts[s - 1] - 2.5
+        hi = np.inf if s == 3 else cuts[s] + 2.5
+        assert ((a[:, 0] >= lo) & (a[:, 0] < hi)).all() and ((b[:, 0] >= lo) & (b[:, 0] < hi)).all()
+        assert abs(len(a) - (len(Xf) / 4 + (0.05 if 0 < s < 3 else 0.025) * len(Xf))) < 0.03 * len(Xf)
+
+
 _GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])

@@ -442,3 +442,56 @@ def test_full_size_properties(gpu):
     res2 = sb.register(X_fix, X_mov, correspondences=100_000, rbp_observed_values=tuple(obs_deg),
                        normals=None)
     assert res2.iterations <= 6 and np.linalg.norm(res2.H - res.H) < 2e-4
+
+
+def test_cli_matches_reference_flags(gpu, tmp_path):
+    """sicp_cli: the reference CLIs' flag set (c++/src/simpleicp-cli.cpp:15-35) on .xyz files;
+    prints the reference's table, H and the `Finished in` line scripts/benchmark.sh greps."""
+    import re
+    import subprocess
+
+    from conftest import REPO
+
+    cli = REPO / "simpleicp_b200" / "sicp_cli"
+    assert cli.exists()
+    for name, extra in (("dragon", []), ("bunny", ["-o", "1"])):
+        g = load_golden(name)
+        X_fix, X_mov = load_pair(name)
+        f1, f2, fo = tmp_path / f"{name}1.xyz", tmp_path / f"{name}2.xyz", tmp_path / f"{name}_out.xyz"
+        sb.write_xyz(f1, X_fix, decimals=4, header=False)
+        sb.write_xyz(f2, X_mov, decimals=4, header=True)
+        r = subprocess.run([str(cli), "-f", str(f1), "-m", str(f2), "-c", "1000", "-n", "10", "-p", "0.3",
+                            "-i", "1", "-x", "100", "--out", str(fo)] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        rows = re.findall(r"^\[\s*(-?[\d.]+)\s+(-?[\d.]+)\s+(-?[\d.]+)\s+(-?[\d.]+)\]$", r.stdout, re.M)
+        H = np.array(rows, dtype=float)
+        assert H.shape == (4, 4)
+        assert np.abs(H - g["H"]).max() < (2e-6 if name == "dragon" else 2e-5)
+        assert re.search(r"Finished in \d+\.\d{3} seconds!", r.stdout)
+        assert "Iteration | correspondences" in r.stdout and "orig:0" in r.stdout
+        X_t = sb.read_xyz(fo)
+        np.testing.assert_allclose(X_t, O.transform_by_H(X_mov, g["H"]), atol=2e-4)
+    bad = subprocess.run([str(cli), "-f", str(tmp_path / "nope.xyz"), "-m", str(f2)], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Caught exception" in bad.stderr
+
+
+def test_batch_of_pairs_matches_individual_runs(gpu):
+    """simpleicp_batch (concurrent engines on separate streams) == one register() per pair; the
+    slab tiler produces independent registrations that all recover the common transform."""
+    pairs = []
+    for i in range(6):
+        Xf = O.surface(40_000, 10_000 + 2 * i, extent=30.0)
+        Ht = O.rbp_to_H([0.004 * (i + 1), -0.003, 0.005, 0.05, -0.03 * i, 0.02])
+        Xm = O.transform_by_H(O.surface(40_000, 10_001 + 2 * i, extent=30.0), np.linalg.inv(Ht))
+        pairs.append((Xf, Xm))
+    table = sb.simpleicp_batch(pairs, concurrency=3)
+    assert table.shape == (6, 20)
+    for i, (Xf, Xm) in enumerate(pairs):
+        r = sb.register(Xf, Xm)
+        np.testing.assert_allclose(table[i, :16].reshape(4, 4), r.H, rtol=0, atol=1e-12)
+        assert table[i, 16] == r.iterations and table[i, 17] == r.records[-1]["n_kept"]
+    X_fix, X_mov, H_true = O.c3_pair(200_000)
+    slabs = sb.tile_slabs(X_fix, X_mov, 4, overlap=5.0)
+    tab = sb.simpleicp_batch(slabs, correspondences=2000)
+    for i in range(4):
+        assert np.linalg.norm(tab[i, :16].reshape(4, 4) - H_true) < 5e-2
