@@ -107,6 +107,9 @@ struct Ctx {
   DevBuf<unsigned char> flush_buf;        // 256 MiB scratch for cold-L2 measurements
   DevBuf<unsigned long long> phase_t;     // %globaltimer stamps of the reject/solve kernel
   DevBuf<unsigned int> grid_bar;          // grid barrier of the cooperative reject/solve kernel
+  DevBuf<unsigned int> lin_hist;          // predictor histogram (match kernels -> reject kernel)
+  bool lin_hist_pending = false;          // filled by a match, not yet consumed by a reject
+  bool lin_hist_init = false;
   sicp_iter_record* rec_host = nullptr;  // pinned
   double* scal_host = nullptr;           // pinned staging for small reads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

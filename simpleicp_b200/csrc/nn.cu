@@ -109,11 +109,20 @@ __device__ __forceinline__ double plane_distance(const Rigid& T, const double* _
                    __dmul_rn(dz, (double)nrm.z));
 }
 
+// Feed the predictor histogram of the reject kernel (reject_solve.cuh: lh_bin): one spread-out
+// atomic per planarity survivor instead of a separate pass over the distances later.
+__device__ __forceinline__ void lin_hist_add(const DevState* st, unsigned int* lin_hist,
+                                             float planarity, double d) {
+  if (lin_hist != nullptr && st->pred_valid && (double)planarity >= st->pred_minpl)
+    atomicAdd(&lin_hist[lh_bin(d, st->pred_med, st->pred_mad)], 1u);
+}
+
 __global__ void __launch_bounds__(128)
     k_match_grid(GridView g, const DevState* __restrict__ st, const double* __restrict__ q_xyz,
                  const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz, long long K,
                  int rmax, int with_distance, long long* __restrict__ nn_idx,
-                 double* __restrict__ out, unsigned int* __restrict__ unresolved) {
+                 double* __restrict__ out, unsigned int* __restrict__ unresolved,
+                 unsigned int* __restrict__ lin_hist) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= K || st->stop) return;
   const Rigid Tinv = st->Tinv;
@@ -129,7 +138,14 @@ __global__ void __launch_bounds__(128)
     return;
   }
   nn_idx[i] = bidx;
-  out[i] = with_distance ? plane_distance(st->T, mov_xyz, bidx, px, py, pz, q_nrm[i]) : best;
+  if (with_distance) {
+    const float4 nr = q_nrm[i];
+    const double d = plane_distance(st->T, mov_xyz, bidx, px, py, pz, nr);
+    out[i] = d;
+    lin_hist_add(st, lin_hist, nr.w, d);
+  } else {
+    out[i] = best;
+  }
 }
 
 // Cooperative variant: MG lanes share one query.  In ring 1 every lane owns one of the 9 grid
@@ -143,7 +159,8 @@ __global__ void __launch_bounds__(128)
     k_match_grid_coop(GridView g, const DevState* __restrict__ st, const double* __restrict__ q_xyz,
                       const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz,
                       long long K, int rmax, int with_distance, long long* __restrict__ nn_idx,
-                      double* __restrict__ out, unsigned int* __restrict__ unresolved) {
+                      double* __restrict__ out, unsigned int* __restrict__ unresolved,
+                      unsigned int* __restrict__ lin_hist) {
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long qi = gt / MG;
   const int sub = threadIdx.x & (MG - 1);
@@ -265,7 +282,14 @@ __global__ void __launch_bounds__(128)
     return;
   }
   nn_idx[qi] = bidx;
-  out[qi] = with_distance ? plane_distance(st->T, mov_xyz, bidx, px, py, pz, q_nrm[qi]) : best;
+  if (with_distance) {
+    const float4 nr = q_nrm[qi];
+    const double d = plane_distance(st->T, mov_xyz, bidx, px, py, pz, nr);
+    out[qi] = d;
+    lin_hist_add(st, lin_hist, nr.w, d);
+  } else {
+    out[qi] = best;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -494,7 +518,8 @@ __global__ void __launch_bounds__(128)
                   const DevState* __restrict__ st, const double* __restrict__ q_xyz,
                   const float4* __restrict__ q_nrm,
                   const double* __restrict__ mov_xyz, int with_distance,
-                  long long* __restrict__ nn_idx, double* __restrict__ out) {
+                  long long* __restrict__ nn_idx, double* __restrict__ out,
+                  unsigned int* __restrict__ lin_hist) {
   const long long nq = qlist ? (long long)(*qcount_ptr) : q_total;
   const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (qi >= nq || st->stop) return;
@@ -510,9 +535,14 @@ __global__ void __launch_bounds__(128)
   }
   const long long q = qlist ? (long long)qlist[qi] : qi;
   nn_idx[q] = ix;
-  out[q] = with_distance ? plane_distance(T, mov_xyz, ix, q_xyz[3 * q + 0], q_xyz[3 * q + 1],
-                                          q_xyz[3 * q + 2], q_nrm[q])
-                         : d;
+  if (with_distance) {
+    const float4 nr = q_nrm[q];
+    const double dd = plane_distance(T, mov_xyz, ix, q_xyz[3 * q + 0], q_xyz[3 * q + 1], q_xyz[3 * q + 2], nr);
+    out[q] = dd;
+    lin_hist_add(st, lin_hist, nr.w, dd);
+  } else {
+    out[q] = d;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -570,13 +600,21 @@ static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
       partials);
   k_bf_finalize<<<(unsigned)((q_total + 127) / 128), 128, 0, c.stream>>>(
       partials, n_chunks, q_total, qlist, qcount, c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p,
-      with_distance ? 1 : 0, c.nn_idx.p, out);
+      with_distance ? 1 : 0, c.nn_idx.p, out, with_distance ? c.lin_hist.p : nullptr);
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 2;
 }
 
 void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, bool allow_bf) {
   const long long K = c.K;
+  // predictor histogram for the reject kernel: zero it if an earlier match filled it and no
+  // reject consumed it (the reject kernel itself leaves it zeroed)
+  c.lin_hist.reserve(LH_BINS + 2);
+  if (with_distance && (c.lin_hist_pending || !c.lin_hist_init)) {
+    SICP_CUDA(cudaMemsetAsync(c.lin_hist.p, 0, (LH_BINS + 2) * sizeof(unsigned int), c.stream));
+    c.lin_hist_init = true;
+  }
+  unsigned int* lh = with_distance ? c.lin_hist.p : nullptr;
   c.nn_idx.reserve(K);
   c.dist.reserve(K);
   c.unresolved.reserve(K + 1);
@@ -584,6 +622,7 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   if (c.nn_engine == SICP_NN_BRUTE) {
     bf_launch(c, with_distance, out, true);
     if (mid) SICP_CUDA(cudaEventRecord(mid, c.stream));
+    if (with_distance) c.lin_hist_pending = true;
     return;
   }
   SICP_CUDA(cudaMemsetAsync(c.unresolved.p + K, 0, sizeof(unsigned int), c.stream));
@@ -592,7 +631,7 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   if (c.match_group == 1) {
     k_match_grid<<<(unsigned)((K + 127) / 128), 128, 0, c.stream>>>(
         c.gmov.view(), c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p, K, rmax,
-        with_distance ? 1 : 0, c.nn_idx.p, out, c.unresolved.p);
+        with_distance ? 1 : 0, c.nn_idx.p, out, c.unresolved.p, lh);
   } else {
     // lanes per query: 16 while the search is latency-bound (few queries), fewer once there are
     // enough queries to fill the machine and issue slots become the limit
@@ -604,7 +643,7 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   k_match_grid_coop<N><<<blocks, 128, 0, c.stream>>>(c.gmov.view(), c.dev_state.p, c.q_xyz.p, \
                                                     c.q_nrm.p, c.mov_xyz.p, K, rmax,          \
                                                     with_distance ? 1 : 0, c.nn_idx.p, out,   \
-                                                    c.unresolved.p)
+                                                    c.unresolved.p, lh)
     if (mg == 4) SICP_LAUNCH_COOP(4);
     else if (mg == 8) SICP_LAUNCH_COOP(8);
     else SICP_LAUNCH_COOP(16);
@@ -614,6 +653,7 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   c.tm.kernel_launches += 1;
   if (mid) SICP_CUDA(cudaEventRecord(mid, c.stream));
   if (use_bf) bf_launch(c, with_distance, out, false);
+  if (with_distance) c.lin_hist_pending = true;
 }
 
 }  // namespace sicp

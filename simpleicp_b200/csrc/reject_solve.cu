@@ -45,7 +45,8 @@ __device__ __constant__ int kShift[RS_LEVELS] = {53, 42, 31, 20, 9, 0};
 __device__ __constant__ int kWidth[RS_LEVELS] = {11, 11, 11, 11, 11, 9};
 
 struct Shared {
-  unsigned int hist[RS_BINS];
+  unsigned int hist[LH_BINS];  // radix histogram (first RS_BINS) or prefix sums of the predictor histogram
+  int lh_i[8];
   unsigned long long sortbuf[RS_CAP];
   double red[RS_WARPS][RS_NACC];
   unsigned int scan_tmp[RS_WARPS];
@@ -168,7 +169,7 @@ __device__ void block_select(Shared& s, const unsigned long long* keys, int cnt,
                              int shift, unsigned long long above, unsigned long long& klo,
                              unsigned long long& khi) {
   const int tid = threadIdx.x, lane = tid & 31;
-  const unsigned long long lowmask = (1ull << shift) - 1ull;  // shift <= 53 here
+  const unsigned long long lowmask = (shift >= 64) ? ~0ull : ((1ull << shift) - 1ull);
   unsigned long long prefix = 0;
   int bits = shift;
   unsigned int n = (unsigned int)cnt;
@@ -668,6 +669,154 @@ __device__ void uncertainties(const RSArgs& a, const double* An, double w, const
   sigma[lane] = (ok && is_free) ? sqrt(s02 * mine) : nan("");
 }
 
+// Median and MAD from the predictor histogram the match kernel filled (reject_solve.cuh:
+// lh_bin): LH_BINS linear bins centred on the previous median, +-4 previous MADs wide.
+//   * the bins holding the two middle ranks give the median candidates;
+//   * with med somewhere in those bins, an element delta bins away has |d - med| inside
+//     ((delta-1) w, (delta+g+1) w), so cumulative symmetric counts N_in(t) bracket the MAD ranks:
+//     everything closer than t_lo - g bins is certainly below the MAD (counted, not gathered),
+//     everything farther than t_hi + g + 1 bins certainly above; the bins in between are the
+//     MAD candidates.
+// One gather pass + one grid barrier then yields both order statistics exactly (same values as
+// the radix path).  Returns false — before touching global state — when the prediction does not
+// bracket the ranks (first iteration, large change, too many candidates): the caller falls back.
+template <bool MULTI>
+__device__ bool predicted_median_mad(Shared& s, const RSArgs& a, RSWork wk, const DevState* st,
+                                     unsigned int& n1_out, double& median, double& mad) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double pm = st->pred_med, pd = st->pred_mad;
+  constexpr int PER = (LH_BINS + RS_THREADS - 1) / RS_THREADS;
+  const int b0 = tid * PER;
+  unsigned int v[PER], sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int b = b0 + j;
+    v[j] = (b < LH_BINS) ? wk.lin_hist[b] : 0u;
+    sum += v[j];
+  }
+  unsigned int incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s.scan_tmp[warp] = incl;
+  __syncthreads();
+  unsigned int woff = 0, total_in = 0;
+  for (int i = 0; i < RS_WARPS; ++i) {
+    if (i < warp) woff += s.scan_tmp[i];
+    total_in += s.scan_tmp[i];
+  }
+  {
+    unsigned int run = woff + incl - sum;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      run += v[j];
+      if (b0 + j < LH_BINS) s.hist[b0 + j] = run;  // inclusive prefix sums
+    }
+  }
+  if (tid == 0) {
+    s.lh_i[0] = -1;
+    s.lh_i[1] = -1;
+    s.lh_i[2] = LH_BINS + 1;  // t_hi (min over t)
+    s.lh_i[3] = -1;           // t_lo (max over t)
+  }
+  __syncthreads();
+  const unsigned int* P = s.hist;
+  const unsigned int under = wk.lin_hist[LH_BINS], over = wk.lin_hist[LH_BINS + 1];
+  const unsigned int n1 = under + total_in + over;
+  n1_out = n1;
+  if (n1 == 0) return true;
+  const unsigned int k = (n1 - 1) >> 1;
+  const bool even = ((n1 & 1u) == 0u);
+  const unsigned int k2 = k + (even ? 1u : 0u);
+  if (k < under || k2 >= under + total_in) return false;
+  const unsigned int r = k - under, r2 = k2 - under;
+  // bins of the two middle ranks: first b with P[b] > r
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int b = b0 + j;
+    if (b < LH_BINS) {
+      const unsigned int pb = P[b], pa = (b > 0) ? P[b - 1] : 0u;
+      if (pa <= r && r < pb) s.lh_i[0] = b;
+      if (pa <= r2 && r2 < pb) s.lh_i[1] = b;
+    }
+  }
+  __syncthreads();
+  const int bm = s.lh_i[0], bm2 = s.lh_i[1];
+  if (bm < 0 || bm2 < bm) return false;
+  const int g = bm2 - bm;
+  if (g > 4) return false;
+  const unsigned int below_m = (bm > 0) ? P[bm - 1] : 0u;
+  const unsigned int cnt_med = P[bm2] - below_m;
+  if (cnt_med > (unsigned int)(RS_CAP - 2)) return false;
+  const unsigned int kA = r - below_m;
+  auto Nin = [&](int t) -> unsigned int {
+    const int hi = min(bm2 + t, LH_BINS - 1), lo = bm - t - 1;
+    return P[hi] - ((lo >= 0) ? P[lo] : 0u);
+  };
+  int tmin = LH_BINS + 1, tmax = -1;
+  for (int t = tid; t <= LH_BINS; t += RS_THREADS) {
+    const unsigned int nin = Nin(t);
+    if (nin >= k2 + 1u) tmin = min(tmin, t);
+    if (nin <= k) tmax = max(tmax, t);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  }
+  if (lane == 0) {
+    atomicMin(&s.lh_i[2], tmin);
+    atomicMax(&s.lh_i[3], tmax);
+  }
+  __syncthreads();
+  const int t_hi = s.lh_i[2], t_lo = s.lh_i[3];
+  if (t_hi > LH_BINS) return false;
+  const int e_lo = max(t_lo - g, 0), e_hi = t_hi + g + 1;
+  if (bm - e_hi < 0 || bm2 + e_hi > LH_BINS - 1) return false;  // candidates must be regular bins
+  const unsigned int n_inner = (t_lo - g - 1 >= 0) ? Nin(t_lo - g - 1) : 0u;
+  const unsigned int cnt_edge = Nin(e_hi) - n_inner;
+  if (cnt_edge > (unsigned int)(RS_CAP - 2) || k < n_inner || k2 - n_inner >= cnt_edge) return false;
+  const unsigned int kM = k - n_inner;
+  __syncthreads();
+
+  // ---- the one gather pass
+  unsigned long long* cand_med = wk.cand;
+  unsigned long long* cand_edge = wk.cand + RS_CAP;
+  for (long long i = blockIdx.x * (long long)RS_THREADS + tid; i < a.K; i += (long long)gridDim.x * RS_THREADS) {
+    if ((double)a.q_nrm[i].w >= a.min_planarity) {
+      const double d = a.dist[i];
+      const int b = lh_bin(d, pm, pd);
+      if (b < LH_BINS) {
+        const int delta = (b < bm) ? (bm - b) : ((b > bm2) ? (b - bm2) : 0);
+        if (delta == 0) cand_med[atomicAdd(&wk.counters[0], 1u)] = f64_to_key(d);
+        if (delta >= e_lo && delta <= e_hi)
+          cand_edge[atomicAdd(&wk.counters[1], 1u)] = (unsigned long long)__double_as_longlong(d);
+      }
+    }
+  }
+  gsync<MULTI>(wk.barrier);
+  if (blockIdx.x == 0 && tid == 0) {
+    wk.phase_t[10] = global_timer_ns();
+    wk.phase_t[24] = 0;
+    wk.phase_t[25] = 0;
+    wk.phase_t[26] = cnt_med;
+    wk.phase_t[27] = cnt_edge;
+  }
+  unsigned long long klo, khi;
+  for (int t = tid; t < (int)cnt_med; t += RS_THREADS) s.sortbuf[t] = cand_med[t];
+  __syncthreads();
+  block_select(s, s.sortbuf, (int)cnt_med, kA, 64, ~0ull, klo, khi);
+  median = even ? 0.5 * (key_to_f64(klo) + key_to_f64(khi)) : key_to_f64(klo);
+  __syncthreads();
+  for (int t = tid; t < (int)cnt_edge; t += RS_THREADS)
+    s.sortbuf[t] = f64_to_key(fabs(__longlong_as_double((long long)cand_edge[t]) - median));
+  __syncthreads();
+  block_select(s, s.sortbuf, (int)cnt_edge, kM, 64, ~0ull, klo, khi);
+  mad = even ? 0.5 * (key_to_f64(klo) + key_to_f64(khi)) : key_to_f64(klo);
+  __syncthreads();
+  return true;
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork wk) {
   __shared__ Shared s;
@@ -686,15 +835,34 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       wk.minkey_other[tid] = ~0ull;
     }
   }
-  if (st->stop) return;  // a previous iteration already met the stop rule
+  if (st->stop) {  // a previous iteration already met the stop rule
+    for (int i = blockIdx.x * RS_THREADS + tid; i < LH_BINS + 2; i += G * RS_THREADS) wk.lin_hist[i] = 0;
+    return;
+  }
 #define RS_STAMP(i) do { if (blockIdx.x == 0 && tid == 0) wk.phase_t[i] = global_timer_ns(); } while (0)
   RS_STAMP(0);
 
-  // ---- A: median
+  // ---- A + B: median and MAD of the planarity survivors
   unsigned int n1 = 0;
-  radix_median<MULTI, 0>(s, a, wk, 0.0, n1);
+  double median = 0.0, mad = 0.0;
+  bool fast = false;
+  if (a.hist_expected && st->pred_valid && st->pred_minpl == a.min_planarity && st->pred_mad > 0.0)
+    fast = predicted_median_mad<MULTI>(s, a, wk, st, n1, median, mad);
   sicp_iter_record* rec = a.rec;
+  if (!fast) {
+    __syncthreads();
+    radix_median<MULTI, 0>(s, a, wk, 0.0, n1);
+    if (n1 != 0) {
+      median = 0.5 * (s.bc[0] + s.bc[1]);
+      __syncthreads();
+      RS_STAMP(1);
+      unsigned int n1b = 0;
+      radix_median<MULTI, 1>(s, a, wk, median, n1b);
+      mad = 0.5 * (s.bc[0] + s.bc[1]);
+    }
+  }
   if (n1 == 0) {
+    for (int i = blockIdx.x * RS_THREADS + tid; i < LH_BINS + 2; i += G * RS_THREADS) wk.lin_hist[i] = 0;
     if (blockIdx.x == 0 && tid == 0) {
       rec->n_kept = 0;
       rec->median = rec->mad = nan("");
@@ -702,16 +870,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     }
     return;
   }
-  const double median = 0.5 * (s.bc[0] + s.bc[1]);
-  __syncthreads();
-  RS_STAMP(1);
-  // ---- B: MAD
-  unsigned int n1b = 0;
-  radix_median<MULTI, 1>(s, a, wk, median, n1b);
-  const double mad = 0.5 * (s.bc[0] + s.bc[1]);
   const double lim = 3.0 * mad;
   __syncthreads();
+  if (fast) RS_STAMP(1);
   RS_STAMP(2);
+  if (blockIdx.x == 0 && tid == 0) wk.phase_t[28] = fast ? 1 : 0;
+  // the predictor histogram has been consumed (or was not usable): leave it zeroed for the next match
+  for (int i = blockIdx.x * RS_THREADS + tid; i < LH_BINS + 2; i += G * RS_THREADS) wk.lin_hist[i] = 0;
 
   // ---- C: keep flags + moment accumulation
   const Rigid Tin = st->T;
@@ -883,6 +1048,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
         rec->n_kept = n_kept;
         rec->median = median;
         rec->mad = mad;
+        st->pred_med = median;
+        st->pred_mad = mad;
+        st->pred_minpl = a.min_planarity;
+        st->pred_valid = (mad > 0.0 && isfinite(mad) && isfinite(median)) ? 1 : 0;
         rec->mean_dist = mean_d;
         rec->std_dist = sqrt(var_d);
         rec->distance_weight = w;
@@ -1108,6 +1277,13 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
   a.it = it;
   a.do_solve = do_solve ? 1 : 0;
   a.arm_stop = arm_stop ? 1 : 0;
+  c.lin_hist.reserve(LH_BINS + 2);
+  if (!c.lin_hist_init) {
+    SICP_CUDA(cudaMemsetAsync(c.lin_hist.p, 0, (LH_BINS + 2) * sizeof(unsigned int), c.stream));
+    c.lin_hist_init = true;
+  }
+  a.hist_expected = c.lin_hist_pending ? 1 : 0;
+  c.lin_hist_pending = false;  // the kernel leaves the histogram zeroed
 
   RSWork wk;
   wk.hist = c.ws.hist.p + par * hist_n;
@@ -1125,6 +1301,7 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
     SICP_CUDA(cudaMemsetAsync(c.grid_bar.p, 0, 2 * sizeof(unsigned int), c.stream));
   }
   wk.barrier = c.grid_bar.p;
+  wk.lin_hist = c.lin_hist.p;
 
   if (multi) {
     void* args[] = {&a, &wk};

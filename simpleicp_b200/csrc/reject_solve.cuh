@@ -25,7 +25,27 @@ struct DevState {
   int iterations_done;
   int lm_ok;
   int pad;
+  // Predictor for the next iteration's order statistics: the match kernel bins every
+  // point-to-plane distance of a planarity survivor into a linear histogram centred on the
+  // previous median, +-4 previous MADs wide (see lh_bin below).
+  double pred_med, pred_mad, pred_minpl;
+  int pred_valid;   // pred_* describe a finished reject phase of this run
+  int hist_filled;  // the last match filled the linear histogram with the current pred_*
 };
+
+// Linear histogram shared by the match kernels (producers) and k_reject_solve (consumer).
+// LH_BINS regular bins over [med - 4 mad, med + 4 mad), then one underflow and one overflow
+// counter.  The bin function is monotone non-decreasing in d, which is all the exactness of the
+// selection needs; both sides evaluate this very expression.
+constexpr int LH_BINS = 4096;
+__host__ __device__ inline int lh_bin(double d, double med, double mad) {
+  const double lo = med - 4.0 * mad;
+  const double inv_w = (double)LH_BINS / (8.0 * mad);
+  const double t = (d - lo) * inv_w;
+  if (!(t >= 0.0)) return LH_BINS;  // underflow (and NaN)
+  if (t >= (double)LH_BINS) return LH_BINS + 1;
+  return (int)t;
+}
 
 struct RSArgs {
   long long K;
@@ -48,6 +68,7 @@ struct RSArgs {
   int it;
   int do_solve;
   int arm_stop;
+  int hist_expected;  // the preceding match launch fed lin_hist (if the predictor was valid)
 };
 
 struct RSWork {
@@ -61,6 +82,7 @@ struct RSWork {
   double* partials;
   unsigned long long* phase_t;  // 32 x %globaltimer stamps of block 0 (diagnostics)
   unsigned int* barrier;        // {arrival count, generation} of the grid barrier
+  unsigned int* lin_hist;       // LH_BINS + 2 counters filled by the match kernels
 };
 
 #ifdef __CUDACC__

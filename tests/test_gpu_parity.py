@@ -307,6 +307,37 @@ def test_fused_loop_equals_stepwise(gpu):
     np.testing.assert_allclose(a.residuals, b.residuals, rtol=0, atol=1e-12)
 
 
+def test_predicted_histogram_select_is_used_and_exact(gpu):
+    """From the second iteration on, median/MAD come from the predictor histogram the match
+    kernel fills (one gather pass instead of ~6 radix passes).  Same keep masks as NumPy."""
+    for name, K in (("dragon", 1000), ("dragon", 20000)):
+        X_fix, X_mov = load_pair(name)
+        with _capi.Engine() as e:
+            res = sb.register(X_fix, X_mov, correspondences=K, engine=e)
+            assert e.phase_times()[28] == 1.0  # last iteration took the fast path
+            lsq = e.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
+            p = e.run_params(0.3, 1.0, 100, lsq)
+            x = np.array(res.rbp.get_parameter_attributes_as_list("estimated_value"))
+            # replay: two queued iterations from the solution; the second uses the fast path
+            e.iterate(p, x_in=x, want_record=True)
+            rec = e.iterate(p, want_record=True)
+            assert e.phase_times()[28] == 1.0
+            # the same state through the stage API (radix path) must give the same statistics
+            H = O.rbp_to_H(np.array(rec.x))
+            xs = x.copy()
+            e.iterate(p, x_in=xs, want_record=True)
+            rec_a = e.iterate(p, want_record=True)      # fast path
+            e.iterate(p, x_in=xs, want_record=True)
+            Hm = O.rbp_to_H(np.array(e.iterate(p, x_in=xs, want_record=True).x))  # state after 1 iteration
+            idx, d = e.match(Hm)                         # resets the predictor -> radix path
+            keep, n_kept, st = e.reject(0.3)
+            # (Hm is rebuilt with NumPy's sin/cos, the device used CUDA's: distances agree to ~1e-16)
+            assert n_kept == rec_a.n_kept
+            np.testing.assert_allclose([st[0], st[1]], [rec_a.median, rec_a.mad], rtol=1e-9, atol=1e-18)
+            S1 = res.normals[3].astype(np.float64) >= 0.3
+            assert st[0] == np.median(d[S1]) and st[1] == np.median(np.abs(d[S1] - st[0]))
+
+
 def test_host_sync_batching_is_equivalent(gpu):
     """Queuing several iterations between host reads (device-side stop flag) changes nothing."""
     g = load_golden("dragon")
