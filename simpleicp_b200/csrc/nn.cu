@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(128)
 // brute-force engine (TMA staged)
 // ------------------------------------------------------------------------------------------
 constexpr int BF_TILE = kBfTile;  // float4 points per stage = 32 KB
-constexpr int BF_STAGES = 4;    // 128 KB of shared memory in flight
+constexpr int BF_STAGES = 3;    // 96 KB of shared memory in flight per block, two blocks per SM
 constexpr int BF_THREADS = 256; // 8 warps
 constexpr int BF_QPW = 8;       // queries per warp
 constexpr int BF_QPB = BF_QPW * (BF_THREADS / 32);
@@ -343,18 +343,17 @@ struct BfPartial {
   long long idx;
 };
 
-// float32 filter margin: |d32 - d_true| <= e(d) for every point, with eta the per-coordinate
-// rounding error of the centred float32 coordinates (see DESIGN.md "brute-force exactness").
-__device__ __forceinline__ float bf_threshold(float best32, double eta) {
-  const double d = (double)best32;
-  const double e = 4.0 * eta * sqrt(d) + 1.0e-6 * d + 4.0 * eta * eta;
-  const double t = d + 2.5 * e;
-  float f = (float)t;
-  if ((double)f < t) f = nextafterf(f, 3.0e38f);
-  return f;
+// float32 filter margin.  Centred float32 coordinates carry a per-coordinate error
+// eta <= 2^-23 (|a|_inf + R) * 1.5 (a = centred query, R = cloud half-extent); the float32
+// squared distance then differs from the true one by at most e(d) = 4 eta sqrt(d) + 1e-6 d +
+// 4 eta^2.  A point is re-evaluated in float64 iff d32 <= best32 + 2.5 e(best32), which the
+// true nearest neighbour always satisfies.  The threshold is evaluated in float32 with its
+// constants rounded up (cA = 10 eta, cC = 10 eta^2, 4e-6 >= 2.5e-6 + rounding).
+__device__ __forceinline__ float bf_threshold(float best32, float cA, float cC) {
+  return fmaf(cA, sqrtf(best32), fmaf(4.0e-6f, best32, best32)) + cC;
 }
 
-__global__ void __launch_bounds__(BF_THREADS, 1)
+__global__ void __launch_bounds__(BF_THREADS, 2)
     k_bf_nn(const float4* __restrict__ mov_f4, const double* __restrict__ mov_xyz, long long n_mov,
             long long n_pad, double cx, double cy, double cz, double radius,
             const DevState* __restrict__ st,
@@ -389,9 +388,9 @@ __global__ void __launch_bounds__(BF_THREADS, 1)
   uint32_t it_base = 0;  // tiles consumed so far by this block (across query groups)
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     // ---- queries of this warp: move into the movable frame, centre, round to float32
-    float ax[BF_QPW], ay[BF_QPW], az[BF_QPW], best32[BF_QPW], thr[BF_QPW];
-    double best64[BF_QPW], eta[BF_QPW];
-    long long bidx[BF_QPW];
+    float ax[BF_QPW], ay[BF_QPW], az[BF_QPW], best32[BF_QPW], thr[BF_QPW], cA[BF_QPW], cC[BF_QPW];
+    double best64[BF_QPW];
+    int bidx[BF_QPW];
 #pragma unroll
     for (int k = 0; k < BF_QPW; ++k) {
       const long long qi = grp * BF_QPB + warp * BF_QPW + k;
@@ -409,7 +408,9 @@ __global__ void __launch_bounds__(BF_THREADS, 1)
       ax[k] = (float)a0;
       ay[k] = (float)a1;
       az[k] = (float)a2;
-      eta[k] = 1.1920929e-7 * (fmax(fabs(a0), fmax(fabs(a1), fabs(a2))) + radius) * 1.5;
+      const double eta = 1.1920929e-7 * (fmax(fabs(a0), fmax(fabs(a1), fabs(a2))) + radius) * 1.5;
+      cA[k] = nextafterf((float)(10.0 * eta), 3.0e38f);
+      cC[k] = nextafterf((float)(10.0 * eta * eta), 3.0e38f);
       best32[k] = 3.0e38f;
       thr[k] = 3.0e38f;
       best64[k] = kInf;
@@ -435,43 +436,60 @@ __global__ void __launch_bounds__(BF_THREADS, 1)
       mbar_wait(&full[s], (g_it / BF_STAGES) & 1);
       const float4* __restrict__ tp = tiles + (size_t)s * BF_TILE;
       const long long base = (tile0 + t) * BF_TILE;
+      unsigned int improved = 0;  // bit k: this lane lowered best32[k] in this tile
 #pragma unroll 2
       for (int j = lane; j < BF_TILE; j += 32) {
         const float4 p = tp[j];  // conflict-free LDS.128
+        float dk[BF_QPW];
+        bool hit = false;
 #pragma unroll
         for (int k = 0; k < BF_QPW; ++k) {
           const float dx = p.x - ax[k], dy = p.y - ay[k], dz = p.z - az[k];
-          const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          if (d <= thr[k]) {
-            // rare: exact float64 re-evaluation from the original coordinates
-            const long long gi = base + j;
-            if (gi < n_mov) {
-              const double* qq = &q64[(warp * BF_QPW + k) * 3];
-              const double ex = mov_xyz[3 * gi + 0] - qq[0];
-              const double ey = mov_xyz[3 * gi + 1] - qq[1];
-              const double ez = mov_xyz[3 * gi + 2] - qq[2];
-              const double d64 = ex * ex + ey * ey + ez * ez;
-              if (d64 < best64[k] || (d64 == best64[k] && gi < bidx[k])) {
-                best64[k] = d64;
-                bidx[k] = gi;
-              }
-              if (d < best32[k]) {
-                best32[k] = d;
-                thr[k] = bf_threshold(d, eta[k]);
+          dk[k] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          hit = hit || (dk[k] <= thr[k]);
+        }
+        if (__builtin_expect(hit, 0)) {
+          // rare: exact float64 re-evaluation from the original coordinates
+          const long long gi = base + j;
+          if (gi < n_mov) {
+            const double gx = mov_xyz[3 * gi + 0], gy = mov_xyz[3 * gi + 1], gz = mov_xyz[3 * gi + 2];
+#pragma unroll
+            for (int k = 0; k < BF_QPW; ++k) {
+              if (dk[k] <= thr[k]) {
+                const double* qq = &q64[(warp * BF_QPW + k) * 3];
+                const double ex = gx - qq[0], ey = gy - qq[1], ez = gz - qq[2];
+                const double d64 = ex * ex + ey * ey + ez * ez;
+                if (d64 < best64[k] || (d64 == best64[k] && (int)gi < bidx[k])) {
+                  best64[k] = d64;
+                  bidx[k] = (int)gi;
+                }
+                if (dk[k] < best32[k]) {
+                  best32[k] = dk[k];
+                  thr[k] = bf_threshold(dk[k], cA[k], cC[k]);
+                  improved |= 1u << k;
+                }
               }
             }
           }
         }
       }
-      // share the float32 bound across the warp so every lane filters with the tightest one
+      // share the float32 bound across the warp, but only for the queries some lane improved in
+      // this tile (after the first tiles that is almost never)
+      unsigned int any = improved;
 #pragma unroll
-      for (int k = 0; k < BF_QPW; ++k) {
-        float m = best32[k];
+      for (int o = 16; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
+      if (any) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (m < best32[k]) {
-          best32[k] = m;
-          thr[k] = bf_threshold(m, eta[k]);
+        for (int k = 0; k < BF_QPW; ++k) {
+          if (any & (1u << k)) {
+            float m = best32[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (m < best32[k]) {
+              best32[k] = m;
+              thr[k] = bf_threshold(m, cA[k], cC[k]);
+            }
+          }
         }
       }
       __syncwarp();
@@ -490,11 +508,11 @@ __global__ void __launch_bounds__(BF_THREADS, 1)
 #pragma unroll
     for (int k = 0; k < BF_QPW; ++k) {
       double d = best64[k];
-      long long ix = bidx[k];
+      int ix = bidx[k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const double od = __shfl_xor_sync(0xffffffffu, d, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, ix, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
         if (od < d || (od == d && oi >= 0 && (ix < 0 || oi < ix))) {
           d = od;
           ix = oi;
