@@ -63,8 +63,12 @@ int32_t sicp_create(int32_t device, void* cuda_stream, sicp_ctx** out);
 int32_t sicp_destroy(sicp_ctx* ctx);
 const char* sicp_last_error(sicp_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
 int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value);
-/*  keys: "nn_engine" (sicp_nn_engine), "sign_mode" (sicp_sign_mode), "grid_target_occupancy",
- *        "grid_max_rings", "host_sync_every" (iterations between host stop-rule reads)         */
+/*  keys: "nn_engine" (sicp_nn_engine), "sign_mode" (sicp_sign_mode), "grid_target_occupancy"
+ *        (points per occupied cell, default 3), "grid_max_rings" (ring limit before the
+ *        brute-force pass takes over, default 8), "grid_sort_cells" (0/1), "host_sync_every"
+ *        (iterations queued between host reads in sicp_run, default 4), "match_group" (lanes per
+ *        query in the grid search: 0 = by K, 1, 4, 8, 16), "rs_blocks" (blocks of the cooperative
+ *        reject/solve kernel, 0 = one per SM)                                                  */
 
 /* ---- clouds: SimpleICP.add_point_clouds (simpleicp.py:58-73) + PointCloud.X ---------------- */
 int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz /*[h|d] n_fix x 3*/, int64_t n_fix,

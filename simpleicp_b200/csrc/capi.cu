@@ -236,6 +236,8 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
   } else if (k == "grid_max_rings") {
     SICP_REQUIRE(value >= 1 && value <= 1e6, SICP_ERR_BAD_ARG, "grid_max_rings out of range");
     c.grid_max_rings = (int)value;
+  } else if (k == "grid_sort_cells") {
+    c.grid_sort_cells = (value != 0) ? 1 : 0;
   } else if (k == "rs_blocks") {
     SICP_REQUIRE(value >= 0 && value <= 256, SICP_ERR_BAD_ARG, "rs_blocks out of range");
     c.rs_blocks = (int)value;
@@ -536,12 +538,17 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
   SICP_CUDA(cudaEventRecord(e0, c.stream));
   int done = 0, fetched = 0, converged = 0;
   DevState h;
+  // host reads: after each of the first two iterations (they decide whether the brute-force
+  // pass is still needed), then every host_sync_every iterations; the device-side stop flag turns
+  // iterations queued past convergence into immediate returns
   const int every = std::max(1, c.host_sync_every);
+  int next_sync = 0;
   c.expect_unresolved = true;
   for (int it = 0; it < p->max_iterations; ++it) {
     match_launch(c, true, nullptr, nullptr, c.expect_unresolved);
     reject_solve_launch(c, *p, it, true, true, it);
-    if ((it + 1) % every == 0 || it + 1 == p->max_iterations) {
+    if (it >= next_sync || it + 1 == p->max_iterations) {
+      next_sync = (it < 2) ? it + 1 : it + every;
       fetch_records(c, fetched, it + 1 - fetched);
       SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
       sync(c);

@@ -58,7 +58,8 @@ struct Ctx {
   int sign_mode = SICP_SIGN_DGEEV;
   double grid_target_occ = 3.0;
   int grid_max_rings = 8;
-  int host_sync_every = 1;
+  int host_sync_every = 4;
+  int grid_sort_cells = 0;  // 1: sort the records inside each cell by index (layout only)
   int rs_blocks = 0;     // blocks of the cooperative reject/solve kernel (0 = one per SM)
   int match_group = 0;   // lanes cooperating on one grid query: 0 = by K, else 1, 4, 8 or 16
 

@@ -311,8 +311,11 @@ void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
   SICP_CUDA(cudaMemsetAsync(g.fill.p, 0, g.n_cells * sizeof(uint32_t), st));
   k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, n, g.cid.p, g.cell_start.p, g.fill.p,
                                                         g.recs.p);
-  k_sort_cells<<<(unsigned)((g.n_cells + 255) / 256), 256, 0, st>>>(g.cell_start.p, g.n_cells,
-                                                                   g.recs.p);
+  // optional: order the records of every cell by original index (reproducible memory layout for
+  // profiling; the search results never depend on it because ties are broken by index)
+  if (c.grid_sort_cells)
+    k_sort_cells<<<(unsigned)((g.n_cells + 255) / 256), 256, 0, st>>>(g.cell_start.p, g.n_cells,
+                                                                     g.recs.p);
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 5;  // bbox x3, scatter, sort_cells
   g.built = true;

@@ -42,15 +42,31 @@ struct TopK {
   }
 };
 
+// four 32-byte records in flight per step (the search is latency-bound); the tail re-reads the
+// last record, which the (distance, index) ordering of the top-k list ignores as a duplicate
 __device__ __forceinline__ void scan_range_k(const Rec* __restrict__ recs, uint32_t s, uint32_t e,
                                              double qx, double qy, double qz, TopK& tk) {
-  for (uint32_t i = s; i < e; ++i) {
-    const Rec r = recs[i];
-    const double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
-    tk.consider(dx * dx + dy * dy + dz * dz, r.idx);
+  for (uint32_t i = s; i < e; i += 4) {
+    const uint32_t last = e - 1;
+    const Rec r0 = recs[i];
+    const Rec r1 = recs[min(i + 1, last)];
+    const Rec r2 = recs[min(i + 2, last)];
+    const Rec r3 = recs[min(i + 3, last)];
+    const int n = (int)min(4u, e - i);
+    const Rec* rr[4] = {&r0, &r1, &r2, &r3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < n) {
+        const double dx = rr[j]->x - qx, dy = rr[j]->y - qy, dz = rr[j]->z - qz;
+        tk.consider(dx * dx + dy * dy + dz * dz, rr[j]->idx);
+      }
+    }
   }
 }
 
+// Exact k-NN by ring expansion.  Rows (x-contiguous cell runs) whose distance bound already
+// exceeds the current k-th best are skipped; ring 1 starts with the query's own row so that the
+// list fills with near points first.
 __device__ void grid_knn(const GridView& g, double qx, double qy, double qz, TopK& tk) {
   const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
   const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
@@ -59,18 +75,26 @@ __device__ void grid_knn(const GridView& g, double qx, double qy, double qz, Top
   for (int r = 1;; ++r) {
     const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
     const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
-    const int za = max(z0, 0), zb = min(z1, g.nz - 1);
-    const int ya = max(y0, 0), yb = min(y1, g.ny - 1);
-    for (int z = za; z <= zb; ++z) {
-      for (int y = ya; y <= yb; ++y) {
-        const long long row = ((long long)z * g.ny + y) * g.nx;
-        const bool full = (r == 1) || z == z0 || z == z1 || y == y0 || y == y1;
-        if (full) {
-          scan_range_k(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, tk);
-        } else {
-          if (x0 >= 0) scan_range_k(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, tk);
-          if (x1 < g.nx) scan_range_k(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, tk);
-        }
+    const int side = 2 * r + 1, items = side * side, centre = items / 2;
+    for (int t0 = 0; t0 < items; ++t0) {
+      // visit the centre row first in ring 1, then the others in order
+      const int t = (r == 1) ? ((t0 == 0) ? centre : ((t0 <= centre) ? t0 - 1 : t0)) : t0;
+      const int dz = t / side - r, dy = t % side - r;
+      const int y = cy + dy, z = cz + dz;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      if (tk.full()) {
+        const double by = (dy < 0) ? qy - (g.oy + (y + 1) * g.h) : ((dy > 0) ? (g.oy + y * g.h) - qy : 0.0);
+        const double bz = (dz < 0) ? qz - (g.oz + (z + 1) * g.h) : ((dz > 0) ? (g.oz + z * g.h) - qz : 0.0);
+        const double lb = fmax(by, 0.0) * fmax(by, 0.0) + fmax(bz, 0.0) * fmax(bz, 0.0);
+        if (lb > tk.worst() * (1.0 + 1e-12)) continue;  // strictly farther: ties are still visited
+      }
+      const long long row = ((long long)z * g.ny + y) * g.nx;
+      const bool full = (r == 1) || dy == -r || dy == r || dz == -r || dz == r;
+      if (full) {
+        scan_range_k(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, tk);
+      } else {
+        if (x0 >= 0) scan_range_k(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, tk);
+        if (x1 < g.nx) scan_range_k(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, tk);
       }
     }
     double guard = kInf;
