@@ -116,7 +116,7 @@ __device__ __forceinline__ void gsync(unsigned int* bar) {
 
 // Find the bin holding rank k in hist (n_bins <= RS_BINS); writes s.k (rank inside the bin),
 // s.cnt (bin count), returns the bin through s.below (count below) and the return value.
-__device__ unsigned int find_bin(Shared& s, const unsigned int* __restrict__ ghist, int n_bins,
+__device__ __noinline__ unsigned int find_bin(Shared& s, const unsigned int* __restrict__ ghist, int n_bins,
                                  unsigned int k, unsigned int* total_out) {
   // each thread owns a contiguous chunk of 6 bins (384 * 6 = 2304 >= 2048)
   constexpr int PER = (RS_BINS + RS_THREADS - 1) / RS_THREADS;
@@ -165,7 +165,7 @@ __device__ unsigned int find_bin(Shared& s, const unsigned int* __restrict__ ghi
 // (0-based) and its successor (`above` when the k-th is the largest).  8-bit radix passes over
 // the shared-memory candidates (__syncthreads only) until <= 32 remain, then one warp ranks
 // them.  Duplicates are handled (all 64 bits fixed -> every remaining candidate is equal).
-__device__ void block_select(Shared& s, const unsigned long long* keys, int cnt, unsigned int k,
+__device__ __noinline__ void block_select(Shared& s, const unsigned long long* keys, int cnt, unsigned int k,
                              int shift, unsigned long long above, unsigned long long& klo,
                              unsigned long long& khi) {
   const int tid = threadIdx.x, lane = tid & 31;
@@ -396,7 +396,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
 // waits at a barrier, so the code is organised to keep that chain short: the three sincos run on
 // three lanes, the matrix products are spread over the lanes, and the 6 x 6 factorisation is a
 // fully unrolled register Cholesky (one rsqrt per pivot, no division, no local memory).
-__device__ void lm_eval(Shared& s, const double* x, const double* cm, const double* cf, int lane) {
+__device__ __noinline__ void lm_eval(Shared& s, const double* x, const double* cm, const double* cf, int lane) {
   double sn = 0.0, cs = 1.0;
   if (lane < 3) sincos(x[lane], &sn, &cs);
   const double s1 = __shfl_sync(0xffffffffu, sn, 0), c1 = __shfl_sync(0xffffffffu, cs, 0);

@@ -526,3 +526,98 @@ def test_batch_of_pairs_matches_individual_runs(gpu):
     tab = sb.simpleicp_batch(slabs, correspondences=2000)
     for i in range(4):
         assert np.linalg.norm(tab[i, :16].reshape(4, 4) - H_true) < 5e-2
+
+
+@pytest.mark.parametrize("K", [4096, 4097])
+def test_kernel_switch_boundary(gpu, K):
+    """K = 4096 runs the single-block reject/solve kernel, 4097 the cooperative one: both must
+    reproduce the oracle (its normals injected) including iteration and kept counts."""
+    X_fix, X_mov = load_pair("dragon")
+    tr = O.Trace()
+    H_o, _, x_o, sig_o, res_o = O.simpleicp(X_fix, X_mov, correspondences=K, trace=tr)
+    nrm = [np.full(X_fix.shape[0], np.nan, dtype=np.float32) for _ in range(4)]
+    for a in range(3):
+        nrm[a][tr.idx_sel] = tr.normals[:, a]
+    nrm[3][tr.idx_sel] = tr.planarity
+    res = sb.register(X_fix, X_mov, correspondences=K, normals=tuple(nrm))
+    assert np.array_equal(res.idx_selected, tr.idx_sel)
+    assert np.linalg.norm(res.H - H_o) < 1e-6
+    assert abs(res.iterations - len(tr.iterations)) <= 3
+    if res.iterations == len(tr.iterations):
+        assert abs(res.records[-1]["n_kept"] - int(tr.iterations[-1].keep.sum())) <= 2
+
+
+def test_small_and_ragged_inputs(gpu):
+    """Tiny clouds, more requested correspondences than points, one-point movable cloud."""
+    rng = np.random.default_rng(3)
+    # 200-point patches of a curved surface, K larger than the cloud -> every point selected
+    def patch(n, seed):
+        r = np.random.default_rng(seed)
+        x, y = r.uniform(0, 1, n), r.uniform(0, 1, n)
+        return np.column_stack((x, y, 0.2 * np.sin(3 * x) * np.cos(2 * y) + 0.05 * x * y))
+    Xf = patch(200, 1)
+    Ht = O.rbp_to_H([0.01, -0.02, 0.015, 0.01, -0.005, 0.008])
+    Xm = O.transform_by_H(patch(300, 2), np.linalg.inv(Ht))
+    H_o, Xt_o, x_o, sig_o, res_o = O.simpleicp(Xf, Xm, correspondences=5000, neighbors=8)
+    res = sb.register(Xf, Xm, correspondences=5000, neighbors=8)
+    assert res.idx_selected.size == 200
+    assert np.linalg.norm(res.H - H_o) < 1e-3  # normals: handful of borderline-sign cases on 200 points
+    # neighbours = number of points (every neighbourhood is the whole cloud)
+    with _capi.Engine() as e:
+        e.set_clouds(Xf[:12], Xm)
+        e.set_selected(None)
+        nx, ny, nz, pl = e.estimate_normals(12)
+        assert np.isfinite(nx).all() and np.allclose(np.abs(nx), np.abs(nx[0]), atol=1e-6)
+        with pytest.raises(_capi.SicpError, match="neighbors"):
+            e.estimate_normals(13)
+        with pytest.raises(_capi.SicpError):
+            e.estimate_normals(1)
+    # a single movable point: every query matches it; too few *distinct* constraints is the
+    # solver's problem, not a crash
+    with _capi.Engine() as e:
+        e.set_clouds(Xf, Xm[:1])
+        e.set_selected(None)
+        e.estimate_normals(8)
+        idx, d = e.match(np.eye(4))
+        assert (idx == 0).all() and np.isfinite(d).all()
+    # empty clouds are rejected at the boundary
+    with _capi.Engine() as e:
+        with pytest.raises(_capi.SicpError):
+            e.set_clouds(np.zeros((0, 3)), Xm)
+        with pytest.raises(ValueError):
+            e.set_clouds(np.zeros((5, 2)), Xm)
+
+
+def test_degenerate_geometry_terminates(gpu):
+    """Two exactly parallel planes leave three of the six parameters unobservable: the
+    reference's trust-region solver returns *some* minimiser; ours must terminate with either a
+    finite result or a clean exception, never hang or return NaN silently."""
+    g = np.stack(np.meshgrid(np.arange(40.0), np.arange(40.0)), -1).reshape(-1, 2)
+    Xf = np.column_stack((g, np.zeros(len(g))))
+    Xm = np.column_stack((g + 0.25, np.full(len(g), 0.1)))
+    try:
+        res = sb.register(Xf, Xm, correspondences=500, max_iterations=5)
+        assert np.isfinite(res.H).all()
+        assert abs(res.H[2, 3] + 0.1) < 1e-6  # the observable part: the plane offset
+    except sb.SimpleICPException as e:
+        assert "singular" in str(e).lower() or "correspondences" in str(e).lower()
+
+
+def test_single_iteration_and_fixed_parameters(gpu):
+    X_fix, X_mov = load_pair("dragon")
+    res = sb.register(X_fix, X_mov, max_iterations=1)
+    assert res.iterations == 1 and not res.converged
+    o = O.simpleicp(X_fix, X_mov, max_iterations=1, normals=(np.column_stack(res.normals[:3]), res.normals[3]))
+    assert np.linalg.norm(res.H - o[0]) < 1e-5
+    # only tz free: x stays at the observed values for the five fixed parameters
+    w = (np.inf,) * 5 + (0.0,)
+    obs = (0.5, -0.25, 1.0, 0.01, -0.02, 0.0)
+    res = sb.register(X_fix, X_mov, rbp_observed_values=obs, rbp_observation_weights=w, max_iterations=3)
+    x = res.rbp.get_parameter_attributes_as_list("estimated_value")
+    np.testing.assert_allclose(x[:3], np.deg2rad(obs[:3]), rtol=0, atol=0)
+    assert x[3] == obs[3] and x[4] == obs[4] and x[5] != 0.0
+    sig = res.rbp.get_parameter_attributes_as_list("estimated_uncertainty")
+    assert np.isnan(sig[:5]).all() and np.isfinite(sig[5])
+    o = O.simpleicp(X_fix, X_mov, rbp_observed_values=obs, rbp_observation_weights=w, max_iterations=3,
+                    normals=(np.column_stack(res.normals[:3]), res.normals[3]))
+    assert abs(x[5] - o[2][5]) < 1e-6
