@@ -189,6 +189,9 @@ int32_t sicp_create(int32_t device, void* cuda_stream, sicp_ctx** out) {
     c.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     SICP_CUDA(cudaEventCreate(&c.ev0));
     SICP_CUDA(cudaEventCreate(&c.ev1));
+    SICP_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    SICP_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+    SICP_CUDA(cudaEventCreateWithFlags(&c.ev_user, cudaEventDisableTiming));
     SICP_CUDA(cudaMallocHost(&c.rec_host, sizeof(sicp_iter_record) * kMaxRecords));
     SICP_CUDA(cudaMallocHost(&c.scal_host, sizeof(double) * 256));
     c.ws.rec.reserve(kMaxRecords);
@@ -214,6 +217,9 @@ int32_t sicp_destroy(sicp_ctx* ctx) {
   cudaStreamSynchronize(c.stream);
   if (c.ev0) cudaEventDestroy(c.ev0);
   if (c.ev1) cudaEventDestroy(c.ev1);
+  if (c.ev_copy) cudaEventDestroy(c.ev_copy);
+  if (c.ev_user) cudaEventDestroy(c.ev_user);
+  if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
   if (c.rec_host) cudaFreeHost(c.rec_host);
   if (c.scal_host) cudaFreeHost(c.scal_host);
   delete ctx;
@@ -289,13 +295,19 @@ int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, con
   SICP_REQUIRE(n_fix < (1ll << 31) && n_mov < (1ll << 31), SICP_ERR_BAD_ARG,
                "clouds are limited to 2^31 - 1 points");
   {
+    // movable cloud on the context's stream; the fixed cloud follows on a second stream (after
+    // everything already queued on the caller's stream) so that its transfer overlaps the grid
+    // build of the movable cloud
     StageTimer t(c, &c.tm.upload_ms);
     c.fix_xyz.reserve(3 * n_fix);
     c.mov_xyz.reserve(3 * n_mov);
-    copy_any(c, c.fix_xyz.p, fix_xyz, sizeof(double) * 3 * n_fix);
     copy_any(c, c.mov_xyz.p, mov_xyz, sizeof(double) * 3 * n_mov);
     t.stop();
   }
+  SICP_CUDA(cudaEventRecord(c.ev_user, c.stream));
+  SICP_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_user, 0));
+  SICP_CUDA(cudaMemcpyAsync(c.fix_xyz.p, fix_xyz, sizeof(double) * 3 * n_fix, cudaMemcpyDefault, c.copy_stream));
+  SICP_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
   c.n_fix = n_fix;
   c.n_mov = n_mov;
   c.gfix.built = false;
@@ -305,6 +317,8 @@ int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, con
     make_float4_copy(c);
     t.stop();
   }
+  SICP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+  SICP_CUDA(cudaStreamSynchronize(c.copy_stream));  // the caller may reuse fix_xyz after return
   c.K = 0;
   c.have_normals = false;
   c.matched = c.rejected = c.solved = false;

@@ -114,6 +114,8 @@ struct Ctx {
   sicp_iter_record* rec_host = nullptr;  // pinned
   double* scal_host = nullptr;           // pinned staging for small reads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;   // second stream: fixed-cloud upload overlaps the movable grid build
+  cudaEvent_t ev_copy = nullptr, ev_user = nullptr;
   sicp_timings tm{};
 
   // staging for host inputs

@@ -140,38 +140,62 @@ __global__ void __launch_bounds__(1024) k_scan_blocksums(uint32_t* __restrict__ 
   }
 }
 
+// Exclusive scan of one 4096-item block, fully coalesced: thread t moves uint4 number j*256 + t
+// (j = 0..3), i.e. 16-byte accesses with unit stride across the warp in both directions; the
+// four 256-wide slabs are scanned one after the other with a running carry.
 __global__ void __launch_bounds__(256) k_scan_down(const uint32_t* __restrict__ in, long long n,
                                                    const uint32_t* __restrict__ block_offsets,
                                                    uint32_t* __restrict__ out) {
-  // each thread owns 16 consecutive items
-  long long base = (long long)blockIdx.x * kScanItems + threadIdx.x * 16;
-  uint32_t v[16];
-  uint32_t s = 0;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    long long i = base + j;
-    v[j] = (i < n) ? in[i] : 0;
-    s += v[j];
-  }
-  // block-wide exclusive scan of s
+  const long long base = (long long)blockIdx.x * kScanItems;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   __shared__ uint32_t wsum[8];
-  uint32_t incl = s;
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) wsum[w] = incl;
-  __syncthreads();
-  uint32_t woff = 0;
-  for (int i = 0; i < w; ++i) woff += wsum[i];
-  uint32_t run = block_offsets[blockIdx.x] + woff + incl - s;
+  __shared__ uint32_t carry_s;
+  uint32_t carry = block_offsets[blockIdx.x];
+  const bool vec_ok = (base + kScanItems <= n) && ((reinterpret_cast<uintptr_t>(in + base) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(out + base) & 15) == 0);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    long long i = base + j;
-    if (i < n) out[i] = run;
-    run += v[j];
+  for (int j = 0; j < 4; ++j) {
+    const long long i0 = base + 4ll * (j * 256 + threadIdx.x);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (vec_ok) {
+      v = *reinterpret_cast<const uint4*>(in + i0);
+    } else {
+      if (i0 + 0 < n) v.x = in[i0 + 0];
+      if (i0 + 1 < n) v.y = in[i0 + 1];
+      if (i0 + 2 < n) v.z = in[i0 + 2];
+      if (i0 + 3 < n) v.w = in[i0 + 3];
+    }
+    const uint32_t s = v.x + v.y + v.z + v.w;
+    uint32_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    __syncthreads();  // wsum / carry_s of the previous slab have been consumed
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+    for (int i = 0; i < 8; ++i) {
+      if (i < w) woff += wsum[i];
+      tot += wsum[i];
+    }
+    uint32_t run = carry + woff + incl - s;
+    uint4 o4;
+    o4.x = run;
+    o4.y = run + v.x;
+    o4.z = o4.y + v.y;
+    o4.w = o4.z + v.z;
+    if (vec_ok) {
+      *reinterpret_cast<uint4*>(out + i0) = o4;
+    } else {
+      if (i0 + 0 < n) out[i0 + 0] = o4.x;
+      if (i0 + 1 < n) out[i0 + 1] = o4.y;
+      if (i0 + 2 < n) out[i0 + 2] = o4.z;
+      if (i0 + 3 < n) out[i0 + 3] = o4.w;
+    }
+    carry += tot;
   }
+  (void)carry_s;
 }
 
 __global__ void k_scan_total(const uint32_t* __restrict__ in, long long n,
