@@ -221,7 +221,7 @@ def run_b200(args):
     # ---- end to end through the public API on pinned host arrays
     def one_e2e():
         res = sb.register(Xf_pin.numpy(), Xm_pin.numpy(), correspondences=K, engine=eng,
-                          transform_out=out_pin.numpy())
+                          transform_out=out_pin.numpy(), want_normals=False)  # = what simpleicp() does
         tab = None
         if world > 1:
             last = res.records[res.iterations - 1]

@@ -274,7 +274,10 @@ class Engine:
                                                    C.byref(n)))
         return keep.astype(bool)
 
-    def estimate_normals(self, neighbors: int):
+    def estimate_normals(self, neighbors: int, download: bool = True):
+        if not download:
+            self._check(self._lib.sicp_estimate_normals(self._h, int(neighbors), None, None, None, None))
+            return None
         out = np.empty((4, self.K), dtype=np.float32)
         self._check(self._lib.sicp_estimate_normals(
             self._h, int(neighbors), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,

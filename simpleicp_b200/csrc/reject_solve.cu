@@ -69,6 +69,7 @@ struct Shared {
   double Ak[36];
   double gk[6];
   double delta[6];
+  double cholL[21];  // factor published for the per-parameter sigma solves
   int spd;
   unsigned long long stamp[2];
   // in-block refinement of the selected radix bin
@@ -470,42 +471,53 @@ __device__ __noinline__ void lm_eval(Shared& s, const double* x, const double* c
   __syncwarp();
 }
 
-// Fully unrolled 6 x 6 Cholesky solve in registers.  A is row-major symmetric positive definite
-// (rows/columns of fixed parameters are identity), b is overwritten with the solution.
-__device__ __forceinline__ bool chol6_solve(const double (&A)[36], double (&b)[6]) {
-  double L[21], inv[6];
+// Warp-cooperative Cholesky of the AUGMENTED 7 x 7 system [[A, b], [b^T, 1]]: lane t < 28 owns
+// entry (ri, cj) of the lower triangle, t = ri (ri + 1) / 2 + cj; rows 0..5 are A, row 6 is the
+// right-hand side, so the factorisation leaves the forward substitution L y = b in row 6.  Every
+// step is a handful of shuffles and one FMA per lane, nothing is indexed dynamically and a lane
+// holds ONE matrix value: the earlier single-lane register version needed the whole matrix plus
+// its factor live at once, overflowed the kernel's 168-register budget and ran out of local
+// memory (4.3 us per solve).  All 32 lanes must call these functions converged.
+__device__ __forceinline__ void tri_coords(int lane, int& ri, int& cj) {
+  const int t = min(lane, 27);
+  int i = 0;
+#pragma unroll
+  for (int r = 1; r < 7; ++r)
+    if (t >= r * (r + 1) / 2) i = r;
+  ri = i;
+  cj = t - i * (i + 1) / 2;
+}
+
+// In: val = this lane's entry of the augmented matrix.  Out: its entry of the factor L (the
+// diagonal holds sqrt(d_j)); inv[j] = 1 / sqrt(d_j) in every lane; returns false when a pivot is
+// not positive (uniform across the warp).
+__device__ __forceinline__ bool warp_chol7_factor(double& val, int ri, int cj, double (&inv)[6]) {
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = A[j * 6 + j];
-#pragma unroll
-    for (int k = 0; k < j; ++k) d = fma(-L[j * (j + 1) / 2 + k], L[j * (j + 1) / 2 + k], d);
+    const double d = __shfl_sync(0xffffffffu, val, j * (j + 1) / 2 + j);
     ok = ok && (d > 0.0) && isfinite(d);
     const double r = rsqrt(d);
     inv[j] = r;
-#pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      double v = A[i * 6 + j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) v = fma(-L[i * (i + 1) / 2 + k], L[j * (j + 1) / 2 + k], v);
-      L[i * (i + 1) / 2 + j] = v * r;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double v = b[i];
-#pragma unroll
-    for (int k = 0; k < i; ++k) v = fma(-L[i * (i + 1) / 2 + k], b[k], v);
-    b[i] = v * inv[i];
-  }
-#pragma unroll
-  for (int i = 5; i >= 0; --i) {
-    double v = b[i];
-#pragma unroll
-    for (int k = i + 1; k < 6; ++k) v = fma(-L[k * (k + 1) / 2 + i], b[k], v);
-    b[i] = v * inv[i];
+    if (cj == j) val *= r;
+    const double lij = __shfl_sync(0xffffffffu, val, ri * (ri + 1) / 2 + j);
+    const double lkj = __shfl_sync(0xffffffffu, val, cj * (cj + 1) / 2 + j);
+    if (cj > j) val = fma(-lij, lkj, val);
   }
   return ok;
+}
+
+// Back substitution L^T x = y on the factored lanes; returns x[lane] in lanes 0..5.
+__device__ __forceinline__ double warp_chol7_backsolve(double val, int lane, int ri, int cj,
+                                                       const double (&inv)[6]) {
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    if (ri == 6 && cj == i) val *= inv[i];
+    const double xi = __shfl_sync(0xffffffffu, val, 21 + i);
+    const double lik = __shfl_sync(0xffffffffu, val, i * (i + 1) / 2 + min(cj, i));
+    if (ri == 6 && cj < i) val = fma(-lik, xi, val);
+  }
+  return __shfl_sync(0xffffffffu, val, 21 + min(lane, 5));
 }
 
 struct LmOut {
@@ -528,6 +540,8 @@ __device__ void lm_solve(Shared& s, const RSArgs& a, double w, const double* x0,
     nf += fre[j] ? 1 : 0;
   }
   const double w2 = w * w;
+  int ri, cj;
+  tri_coords(lane, ri, cj);
   auto obs_cost = [&](const double* xx) {
     double c = 0.0;
 #pragma unroll
@@ -552,27 +566,40 @@ __device__ void lm_solve(Shared& s, const RSArgs& a, double w, const double* x0,
   double lambda = 0.0, rel_prev = 0.0;
   int it = 0, ok = 1;
   for (it = 0; it < 40 && nf > 0; ++it) {
-    if (lane == 0) {
+    {
       // weighted Gauss-Newton system; fixed parameters become identity rows (delta = 0)
-      double Ar[36], br[6];
+      double val;
+      const double wi = a.wobs[min(ri, 5)], wj = a.wobs[min(cj, 5)];
+      const bool fj = isfinite(wj);
+      double xj = 0.0;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j)
-          Ar[i * 6 + j] = (fre[i] && fre[j]) ? w2 * s.Ak[i * 6 + j] : ((i == j) ? 1.0 : 0.0);
-        double gi = fre[i] ? w2 * s.gk[i] : 0.0;
-        if (obsd[i]) {
-          gi += a.wobs[i] * a.wobs[i] * (x[i] - a.obs[i]);
-          Ar[i * 6 + i] += a.wobs[i] * a.wobs[i];
+      for (int k = 0; k < 6; ++k)
+        if (k == cj) xj = x[k];
+      if (ri < 6) {
+        if (!(isfinite(wi) && fj)) {
+          val = (ri == cj) ? 1.0 : 0.0;
+        } else {
+          val = w2 * s.Ak[ri * 6 + cj];
+          if (ri == cj) {
+            if (wi > 0.0) val += wi * wi;
+            val *= (1.0 + lambda);
+          }
         }
-        if (fre[i]) Ar[i * 6 + i] *= (1.0 + lambda);
-        br[i] = -gi;
+      } else if (cj < 6) {
+        double gi = fj ? w2 * s.gk[cj] : 0.0;
+        if (fj && wj > 0.0) gi += wj * wj * (xj - a.obs[cj]);
+        val = -gi;
+      } else {
+        val = 1.0;
       }
-      const bool spd = chol6_solve(Ar, br);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) s.delta[i] = br[i];
-      s.spd = spd ? 1 : 0;
-      if (it == 0) s.stamp[1] = global_timer_ns();
+      double inv[6];
+      const bool spd = warp_chol7_factor(val, ri, cj, inv);
+      const double sol = warp_chol7_backsolve(val, lane, ri, cj, inv);
+      if (lane < 6) s.delta[lane] = sol;
+      if (lane == 0) {
+        s.spd = spd ? 1 : 0;
+        if (it == 0) s.stamp[1] = global_timer_ns();
+      }
     }
     __syncwarp();
     if (!s.spd) {
@@ -632,41 +659,51 @@ __device__ void lm_solve(Shared& s, const RSArgs& a, double w, const double* x0,
 // sigma of the free parameters: Cxx = s0^2 (A^T P A)^-1 in the reference's formulation
 // (optimization.py:147-160): N = w * sum a a^T + diag(w_obs), vPv = w sum r^2 + sum w_obs dx^2.
 // Called by a full warp: lane j < 6 produces sigma[j] (one column of the inverse each).
-__device__ void uncertainties(const RSArgs& a, const double* An, double w, const double* x,
-                              double sum_r2, long long n_kept, int lane, double* sigma) {
-  if (lane >= 6) return;
+__device__ void uncertainties(Shared& s, const RSArgs& a, const double* An, double w,
+                              const double* x, double sum_r2, long long n_kept, int lane,
+                              double* sigma) {
   int nf = 0, nobs = 0;
-  bool fre[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    fre[j] = isfinite(a.wobs[j]);
-    nf += fre[j] ? 1 : 0;
-    nobs += (fre[j] && a.wobs[j] > 0.0) ? 1 : 0;
-  }
   double vPv = w * sum_r2;
 #pragma unroll
-  for (int j = 0; j < 6; ++j)
-    if (fre[j] && a.wobs[j] > 0.0) vPv += a.wobs[j] * (x[j] - a.obs[j]) * (x[j] - a.obs[j]);
-  const double s02 = vPv / (double)(n_kept + nobs - nf);
-  double N[36], e[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-      N[i * 6 + j] = (fre[i] && fre[j]) ? w * An[i * 6 + j] : ((i == j) ? 1.0 : 0.0);
-    if (fre[i] && a.wobs[i] > 0.0) N[i * 6 + i] += a.wobs[i];
-    e[i] = (i == lane) ? 1.0 : 0.0;
+  for (int j = 0; j < 6; ++j) {
+    const bool fj = isfinite(a.wobs[j]);
+    nf += fj ? 1 : 0;
+    if (fj && a.wobs[j] > 0.0) {
+      ++nobs;
+      vPv += a.wobs[j] * (x[j] - a.obs[j]) * (x[j] - a.obs[j]);
+    }
   }
-  const bool ok = chol6_solve(N, e);
-  double mine = 0.0;
+  const double s02 = vPv / (double)(n_kept + nobs - nf);
+  int ri, cj;
+  tri_coords(lane, ri, cj);
+  const double wi = a.wobs[min(ri, 5)], wj = a.wobs[min(cj, 5)];
+  double val = (ri == cj) ? 1.0 : 0.0;
+  if (ri < 6 && isfinite(wi) && isfinite(wj)) {
+    val = w * An[ri * 6 + cj];
+    if (ri == cj && wi > 0.0) val += wi;
+  } else if (ri == 6 && cj < 6) {
+    val = 0.0;
+  }
+  double inv[6];
+  const bool ok = warp_chol7_factor(val, ri, cj, inv);
+  // (N^-1)_jj = |L^-1 e_j|^2: lane j forward-substitutes its own unit vector against the factor,
+  // which the owning lanes publish through shared memory.
+  double* L = s.cholL;
+  if (lane < 21) L[lane] = val;
+  __syncwarp();
+  if (lane < 6) {
+    double y[6], acc = 0.0;
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
-    if (i == lane) mine = e[i];
-  bool is_free = false;
+    for (int i = 0; i < 6; ++i) {
+      double v = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
-    if (i == lane) is_free = fre[i];
-  sigma[lane] = (ok && is_free) ? sqrt(s02 * mine) : nan("");
+      for (int k = 0; k < i; ++k) v = fma(-L[i * (i + 1) / 2 + k], y[k], v);
+      y[i] = v * inv[i];
+      acc = fma(y[i], y[i], acc);
+    }
+    sigma[lane] = (ok && isfinite(a.wobs[lane])) ? sqrt(s02 * acc) : nan("");
+  }
+  __syncwarp();
 }
 
 // Median and MAD from the predictor histogram the match kernel filled (reject_solve.cuh:
@@ -1142,7 +1179,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     const double mean = t0 / (double)n;
     const double sd = sqrt(fmax(t1 / (double)n - mean * mean, 0.0));
     // one lane per parameter: sigma_j, and the new cumulative parameters
-    uncertainties(a, st->An, st->w, st->x_new, t1, n, lane, st->sigma);
+    uncertainties(s, a, st->An, st->w, st->x_new, t1, n, lane, st->sigma);
     if (lane < 6) {
       rec->x[lane] = st->x_new[lane];
       st->x[lane] = st->x_new[lane];

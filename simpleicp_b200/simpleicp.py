@@ -109,6 +109,7 @@ def register(
     transform_out=None,
     stepwise: bool = False,
     on_normals=None,
+    want_normals: bool = True,
 ) -> _Result:
     """Core of both front ends: one registration on one GPU.
 
@@ -155,7 +156,9 @@ def register(
 
         if normals is None:
             _log.info("Estimate normals of selected points ...")
-            nrm = eng.estimate_normals(neighbors)
+            # the normals stay on the device for the loop; they are only downloaded when someone
+            # wants to look at them (the class facade stores them as columns of pc_fix)
+            nrm = eng.estimate_normals(neighbors, download=want_normals or on_normals is not None)
         else:
             nrm = tuple(np.asarray(a, dtype=np.float32)[idx] for a in normals)
             eng.set_normals(*nrm)
@@ -363,5 +366,6 @@ def simpleicp(X_fix, X_mov, **kwargs):
     X_fix / X_mov: (n, 3) float64 NumPy arrays or CUDA torch tensors.  Keyword arguments are
     those of ``SimpleICP.run``.  Inputs are not modified.
     """
+    kwargs.setdefault("want_normals", False)
     res = register(X_fix, X_mov, **kwargs)
     return res.H, res.X_mov_transformed, res.rbp, res.residuals
