@@ -251,6 +251,27 @@ def run_b200(args):
     dH_true = float(np.linalg.norm(res.H - H_true))
     tm = eng.timings()
 
+    # ---- the linearised variant on the same pair: same two kernels
+    # per iteration, one linear solve instead of the Gauss-Newton loop; reported beside the headline
+    variants = None
+    if world == 1:
+        eng.set_option("variant", 1)
+        eng.iterate(params, x_in=np.zeros(6), want_record=True)
+        for _ in range(max(args.warmup, 3)):
+            eng.iterate(params, want_record=True)
+        st_lin = eng.time_stages(params, args.steps, True)
+        t0 = time.perf_counter()
+        rl = sb.simpleicp_linearized(Xf_pin.numpy(), Xm_pin.numpy(), correspondences=K, engine=eng,
+                                     transform_out=out_pin.numpy())
+        torch.cuda.synchronize()
+        lin_s = time.perf_counter() - t0
+        eng.set_option("variant", 0)
+        variants = {"linearized": {
+            "ms_per_step": st_lin["iteration"], "value": K / (st_lin["iteration"] * 1e-3), "unit": UNIT,
+            "kernels_ms_cold_l2": st_lin, "e2e_ms_per_registration": 1e3 * lin_s, "e2e_iterations": rl.iterations,
+            "H_frobenius_vs_H_true": float(np.linalg.norm(rl.T - H_true)),
+            "api": "simpleicp_b200.simpleicp_linearized(X_fix, X_mov, correspondences=K, engine=<reused>)"}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -325,13 +346,13 @@ def run_b200(args):
         "ms_per_step_l2_warm_queued": warm_ms,
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 24,
-                "d2h_bytes_per_step": n * 24 + 8 * n_kept + 4 * 4 * K,
+                "d2h_bytes_per_step": n * 24 + 8 * n_kept,
                 "ms_per_registration": 1e3 * e2e_s / args.e2e_steps, "iterations": its_total / (args.e2e_steps * world),
                 "registrations": args.e2e_steps,
                 "api": "simpleicp_b200.register(X_fix, X_mov, correspondences=K, engine=<reused>, transform_out=<pinned>)",
                 "stage_ms": {k: v for k, v in tm.items() if k.endswith("_ms")},
                 "H_frobenius_vs_H_true": dH_true},
-        "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+        "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "variants": variants,
     }
     print(json.dumps(line))
     if world > 1:

@@ -2,9 +2,11 @@
 // (c++/src/simpleicp-cli.cpp:15-35, rust/src/main.rs:10-46):
 //   -f/--fixed  -m/--movable  -c/--correspondences  -n/--neighbors  -p/--min_planarity
 //   -o/--max_overlap_distance (<= 0: fully overlapping)  -i/--min_change  -x/--max_iterations
-// plus  --out FILE (write the transformed movable cloud)  --device N  --quiet.
-// Semantics are those of the library (the Python reference's: raw MAD, converged non-linear
-// solve).  Prints the reference's iteration table, H and "Finished in N.NNN seconds!" (the line
+// plus  --out FILE (write the transformed movable cloud)  --device N  --quiet  --variant V.
+// --variant python (default): the Python reference's semantics (raw MAD, converged non-linear
+// solve); --variant linearized | cpp: the algorithm of the native reference CLIs themselves (one
+// linear solve per iteration, 1.4826 MAD, sample std; "cpp" also reports H * dH as
+// c++/src/simpleicp.cpp:66 does), see sicp_variant in include/sicp_b200.h.  Prints the reference's iteration table, H and "Finished in N.NNN seconds!" (the line
 // scripts/benchmark.sh:43-51 greps; file I/O excluded from it, as in every reference CLI).
 #include <cfenv>
 #include <chrono>
@@ -31,6 +33,7 @@ static void usage() {
        "  -x, --max_iterations arg        Maximum number of iterations (default: 100)\n"
        "      --out arg                   Write the transformed movable cloud to this .xyz file\n"
        "      --device arg                CUDA device index (default: 0)\n"
+       "      --variant arg               python | linearized | cpp (default: python)\n"
        "      --quiet                     Only print H\n"
        "  -h, --help                      Print usage");
 }
@@ -50,6 +53,7 @@ int main(int argc, char** argv) {
   int neighbors = 10, max_iterations = 100, device = 0;
   double min_planarity = 0.3, max_overlap = -1.0, min_change = 1.0;
   bool quiet = false;
+  int variant = SICP_VARIANT_PYTHON;
   if (argc == 1) {
     usage();
     return 0;
@@ -75,6 +79,13 @@ int main(int argc, char** argv) {
     else if (a == "--out") out = val("--out");
     else if (a == "--device") device = atoi(val("--device"));
     else if (a == "--quiet") quiet = true;
+    else if (a == "--variant") {
+      const std::string v = val("--variant");
+      if (v == "python") variant = SICP_VARIANT_PYTHON;
+      else if (v == "linearized") variant = SICP_VARIANT_LINEARIZED;
+      else if (v == "cpp") variant = SICP_VARIANT_LINEARIZED_CPP;
+      else { fprintf(stderr, "Caught exception: unknown variant '%s'\n", v.c_str()); return 1; }
+    }
     else { fprintf(stderr, "Caught exception: Option '%s' does not exist\n", a.c_str()); return 1; }
   }
   if (fixed.empty() || movable.empty()) {
@@ -93,6 +104,7 @@ int main(int argc, char** argv) {
     return 1;
   }
   const auto t0 = std::chrono::steady_clock::now();
+  CHECK(sicp_set_option(ctx, "variant", (double)variant));
   CHECK(sicp_set_clouds(ctx, xf, nf, xm, nm));
   std::vector<int64_t> idx;
   int64_t m = nf;
@@ -110,13 +122,14 @@ int main(int argc, char** argv) {
   }
   if (!quiet) puts("Select points for correspondences in fixed point cloud ...");
   if (m > correspondences) {
-    // rint(linspace(0, m - 1, n)) with round-half-even (python/simpleicp/pointcloud.py:142-144)
+    // rint(linspace(0, m - 1, n)) with round-half-even (python/simpleicp/pointcloud.py:142-144);
+    // the native CLIs round half away from zero (c++/src/pointcloud.cpp:92-96)
     std::fesetround(FE_TONEAREST);
     std::vector<int64_t> pick((size_t)correspondences);
     const double step = (double)(m - 1) / (double)(correspondences - 1);
     for (long long i = 0; i < correspondences; ++i) {
       const double y = (i == correspondences - 1) ? (double)(m - 1) : (double)i * step;
-      const int64_t p = (int64_t)std::nearbyint(y);
+      const int64_t p = (int64_t)(variant == SICP_VARIANT_PYTHON ? std::nearbyint(y) : std::round(y));
       pick[(size_t)i] = idx.empty() ? p : idx[(size_t)p];
     }
     idx.swap(pick);
@@ -136,7 +149,9 @@ int main(int argc, char** argv) {
   std::vector<sicp_iter_record> log((size_t)max_iterations);
   CHECK(sicp_run(ctx, &p, &res, log.data()));
   std::vector<double> xt((size_t)nm * 3);
-  CHECK(sicp_transform(ctx, res.H, xt.data()));
+  double T[16];
+  CHECK(sicp_get_transform(ctx, T));  // == res.H except for --variant cpp
+  CHECK(sicp_transform(ctx, T, xt.data()));
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (!quiet) {
     const int rows = res.converged ? res.iterations - 1 : res.iterations;

@@ -57,13 +57,30 @@ typedef enum {
   SICP_SIGN_CANONICAL = 1  /* largest-magnitude component positive                              */
 } sicp_sign_mode;
 
+/* Algorithm variant of reject + solve (option key "variant").  The default is the Python package's
+ * algorithm (the north-star path).  The linearised variants restate the C++/Rust/MATLAB/Julia
+ * drivers (c++/src/corrpts.cpp:59-156, c++/src/simpleicp.cpp:54-80, rust/src/icp.rs:135-184):
+ * median/MAD over ALL distances with the upper middle element (std::nth_element at n/2),
+ * sigma = 1.4826 MAD, one linear solve A x = l per iteration, cloud moved by dH = H(euler(x), t),
+ * residuals A x - l, sample standard deviation, no parameter uncertainties and no
+ * observed/fixed parameters.  They differ in the matrix that is REPORTED: dH * H (the transform
+ * really applied to the cloud; Rust rust/src/icp.rs:164, MATLAB matlab/simpleicp.m:55) or H * dH
+ * (the C++ driver, c++/src/simpleicp.cpp:66).  Normals stay in the float32 storage of the
+ * default variant (the C++ code keeps float64), see DESIGN.md.                                  */
+typedef enum {
+  SICP_VARIANT_PYTHON = 0,
+  SICP_VARIANT_LINEARIZED = 1,        /* reports dH * H                                          */
+  SICP_VARIANT_LINEARIZED_CPP = 2     /* reports H * dH                                          */
+} sicp_variant;
+
 /* ---- life cycle --------------------------------------------------------------------------- */
 int32_t sicp_abi_version(void);
 int32_t sicp_create(int32_t device, void* cuda_stream, sicp_ctx** out);
 int32_t sicp_destroy(sicp_ctx* ctx);
 const char* sicp_last_error(sicp_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
 int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value);
-/*  keys: "nn_engine" (sicp_nn_engine), "sign_mode" (sicp_sign_mode), "grid_target_occupancy"
+/*  keys: "nn_engine" (sicp_nn_engine), "sign_mode" (sicp_sign_mode), "variant" (sicp_variant),
+ *        "grid_target_occupancy"
  *        (points per occupied cell, default 3), "grid_max_rings" (ring limit before the
  *        brute-force pass takes over, default 8), "grid_sort_cells" (0/1), "host_sync_every"
  *        (iterations queued between host reads in sicp_run, default 4), "match_group" (lanes per
@@ -160,6 +177,11 @@ typedef struct {
 
 int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out /*[h]*/,
                  sicp_iter_record* log /*[h] max_iterations entries or NULL*/);
+/* The rigid transform the last sicp_run / sicp_solve actually applied to the movable cloud.  Equal
+ * to the result's H except for SICP_VARIANT_LINEARIZED_CPP, whose reported H = H * dH is a
+ * different product of the same increments (c++/src/simpleicp.cpp:62-66: the cloud is moved by
+ * dH on the left, the report multiplies on the right).                                         */
+int32_t sicp_get_transform(sicp_ctx* ctx, double T[16] /*[h]*/);
 /* residuals of the final iteration in kept order (simpleicp.py:324, 4th return value).          */
 int32_t sicp_get_residuals(sicp_ctx* ctx, double* residuals /*[h|d] cap*/, int64_t cap,
                            int64_t* n /*[h]*/);

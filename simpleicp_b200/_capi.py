@@ -25,7 +25,7 @@ SYMBOLS = (
     "sicp_abi_version", "sicp_create", "sicp_destroy", "sicp_last_error", "sicp_set_option",
     "sicp_set_clouds", "sicp_set_selected", "sicp_select_in_range", "sicp_estimate_normals",
     "sicp_set_normals", "sicp_get_knn", "sicp_match", "sicp_reject", "sicp_solve",
-    "sicp_uncertainties", "sicp_run", "sicp_get_residuals", "sicp_iterate", "sicp_transform",
+    "sicp_uncertainties", "sicp_run", "sicp_get_transform", "sicp_get_residuals", "sicp_iterate", "sicp_transform",
     "sicp_get_timings", "sicp_time_stages", "sicp_get_phase_times",
     "sicp_xyz_load", "sicp_xyz_free", "sicp_xyz_save", "sicp_io_last_error",
 )
@@ -102,6 +102,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
                        C.POINTER(dbl), C.POINTER(dbl)],
         "sicp_uncertainties": [vp, C.POINTER(dbl)],
         "sicp_run": [vp, C.POINTER(RunParams), C.POINTER(RunResult), C.POINTER(IterRecord)],
+        "sicp_get_transform": [vp, C.POINTER(C.c_double)],
         "sicp_get_residuals": [vp, vp, i64, C.POINTER(i64)],
         "sicp_iterate": [vp, C.POINTER(RunParams), C.POINTER(dbl), C.POINTER(IterRecord)],
         "sicp_transform": [vp, C.POINTER(dbl), vp],
@@ -351,6 +352,12 @@ class Engine:
         res = np.empty(int(out.n_residuals), dtype=np.float64)
         self._check(self._lib.sicp_get_residuals(self._h, _ptr(res), res.size, C.byref(n)))
         return out, [log[i] for i in range(out.iterations)], res
+
+    def get_transform(self) -> np.ndarray:
+        """The 4 x 4 transform the last run/solve applied to the movable cloud."""
+        T = (C.c_double * 16)()
+        self._check(self._lib.sicp_get_transform(self._h, T))
+        return np.array(T).reshape(4, 4)
 
     def iterate(self, params: RunParams, x_in=None, want_record: bool = False):
         rec = IterRecord() if want_record else None

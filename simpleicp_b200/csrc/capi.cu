@@ -91,6 +91,8 @@ void init_state(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_lo
     for (int j = 0; j < 6; ++j) h.x[j] = x[j];
   h.T = T_or_null ? *T_or_null : rigid_from_x(h.x);
   h.Tinv = rigid_inverse(h.T);
+  h.T_res = h.T;
+  h.H_rep = h.T;
   if (reset_loop) h.stop = 0;
   SICP_CUDA(cudaMemcpyAsync(c.dev_state.p, &h, sizeof(h), cudaMemcpyHostToDevice, c.stream));
   sync(c);
@@ -236,6 +238,9 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
   } else if (k == "sign_mode") {
     SICP_REQUIRE(value == 0 || value == 1, SICP_ERR_BAD_ARG, "sign_mode must be 0 or 1");
     c.sign_mode = (int)value;
+  } else if (k == "variant") {
+    SICP_REQUIRE(value == 0 || value == 1 || value == 2, SICP_ERR_BAD_ARG, "variant must be 0, 1 or 2");
+    c.variant = (int)value;
   } else if (k == "grid_target_occupancy") {
     SICP_REQUIRE(value >= 0.25 && value <= 64, SICP_ERR_BAD_ARG, "grid_target_occupancy out of range");
     c.grid_target_occ = value;
@@ -483,6 +488,7 @@ int32_t sicp_solve(sicp_ctx* ctx, const sicp_lsq_params* lp, double x[6], double
     c.last_sigma[j] = h.sigma[j];
   }
   H_from_rigid(h.T, H);
+  H_from_rigid(h.T, c.last_T);
   if (stats) {
     stats[0] = r.mean_res;
     stats[1] = r.std_res;
@@ -543,6 +549,11 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
   }
   SICP_REQUIRE(any_finite, SICP_ERR_BAD_ARG,
                "At least one element in rbp_observation_weights must be finite.");
+  if (c.variant != SICP_VARIANT_PYTHON)
+    for (int j = 0; j < 6; ++j)
+      SICP_REQUIRE(p->lsq.obs_weight[j] == 0.0, SICP_ERR_BAD_ARG,
+                   "the linearised variants have no observed or fixed parameters: "
+                   "rbp_observation_weights must be all zero");
   init_state(c, p->lsq.x0, nullptr, true);
   std::memset(out, 0, sizeof(*out));
 
@@ -598,12 +609,14 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
   out->iterations = done;
   out->converged = converged;
   for (int j = 0; j < 6; ++j) {
-    out->x[j] = h.x[j];
+    // linearised variants: x holds the increments of the last iteration, H the reported matrix
+    out->x[j] = c.variant ? h.x_new[j] : h.x[j];
     out->sigma[j] = h.sigma[j];
-    c.last_x[j] = h.x[j];
+    c.last_x[j] = out->x[j];
     c.last_sigma[j] = h.sigma[j];
   }
-  H_from_rigid(h.T, out->H);
+  H_from_rigid(c.variant ? h.H_rep : h.T, out->H);
+  H_from_rigid(h.T, c.last_T);
   out->n_residuals = h.n_kept;
   out->loop_ms = ms;
   c.n_kept = h.n_kept;
@@ -611,6 +624,14 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
   c.tm.reject_solve_ms = ms;
   if (log) std::memcpy(log, c.rec_host, sizeof(sicp_iter_record) * done);
   c.matched = c.rejected = c.solved = true;
+  API_END
+}
+
+int32_t sicp_get_transform(sicp_ctx* ctx, double T[16]) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(c.solved, SICP_ERR_STATE, "no solve has been run");
+  SICP_REQUIRE(T != nullptr, SICP_ERR_BAD_ARG, "T is NULL");
+  for (int j = 0; j < 16; ++j) T[j] = c.last_T[j];
   API_END
 }
 

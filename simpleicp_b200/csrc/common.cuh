@@ -137,6 +137,17 @@ __host__ __device__ inline Rigid rigid_from_x(const double* x) {
   return T;
 }
 
+// A after B: p -> A(B(p))
+__host__ __device__ inline Rigid rigid_compose(const Rigid& A, const Rigid& B) {
+  Rigid C;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      C.r[i * 3 + j] = A.r[i * 3 + 0] * B.r[0 * 3 + j] + A.r[i * 3 + 1] * B.r[1 * 3 + j] + A.r[i * 3 + 2] * B.r[2 * 3 + j];
+    C.t[i] = A.r[i * 3 + 0] * B.t[0] + A.r[i * 3 + 1] * B.t[1] + A.r[i * 3 + 2] * B.t[2] + A.t[i];
+  }
+  return C;
+}
+
 inline void H_from_rigid(const Rigid& T, double H[16]) {
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) H[i * 4 + j] = T.r[i * 3 + j];

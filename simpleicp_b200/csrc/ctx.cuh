@@ -56,6 +56,7 @@ struct Ctx {
   // options
   int nn_engine = SICP_NN_AUTO;
   int sign_mode = SICP_SIGN_DGEEV;
+  int variant = SICP_VARIANT_PYTHON;
   double grid_target_occ = 3.0;
   int grid_max_rings = 8;
   int host_sync_every = 4;
@@ -96,6 +97,7 @@ struct Ctx {
 
   // last solve state (for uncertainties)
   double last_x[6] = {0, 0, 0, 0, 0, 0};
+  double last_T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};  // transform applied to the movable cloud
   double last_sigma[6] = {0, 0, 0, 0, 0, 0};
   sicp_lsq_params last_lsq{};
 

@@ -271,7 +271,7 @@ template <bool MULTI, int SEL>
 __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double center,
                              unsigned int& n1_out) {
   const long long K = a.K;
-  const double minpl = a.min_planarity;
+  const double minpl = a.stat_minpl;
   unsigned int* ghist_base = wk.hist + (size_t)SEL * RS_LEVELS * RS_BINS;
   unsigned long long prefix = 0;
   unsigned int k = 0, cnt = 0, n1 = 0;
@@ -397,6 +397,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
 // waits at a barrier, so the code is organised to keep that chain short: the three sincos run on
 // three lanes, the matrix products are spread over the lanes, and the 6 x 6 factorisation is a
 // fully unrolled register Cholesky (one rsqrt per pivot, no division, no local memory).
+__device__ __noinline__ void moment_products(Shared& s, int lane);
 __device__ __noinline__ void lm_eval(Shared& s, const double* x, const double* cm, const double* cf, int lane) {
   double sn = 0.0, cs = 1.0;
   if (lane < 3) sincos(x[lane], &sn, &cs);
@@ -442,6 +443,11 @@ __device__ __noinline__ void lm_eval(Shared& s, const double* x, const double* c
     for (int k = 0; k < 6; ++k) s.J[12][k] = 0.0;
   }
   __syncwarp();
+  moment_products(s, lane);
+}
+
+// A = J^T M J, g = J^T M theta, F = theta^T M theta from s.J / s.th (one warp).
+__device__ __noinline__ void moment_products(Shared& s, int lane) {
   for (int e = lane; e < 91; e += 32) {
     const int r = e / 7, c = e % 7;
     double acc = 0.0;
@@ -656,6 +662,51 @@ __device__ void lm_solve(Shared& s, const RSArgs& a, double w, const double* x0,
   out.ok = ok;
 }
 
+// Linearised variant: ONE solve of A x = l (c++/src/corrpts.cpp:113-156) expressed on the moment
+// matrix.  With p2 = R_c u + c_f (u = movable point minus its centre, c_f = T_c c_m) the
+// reference's row is r(x) = n . ((I + [alpha]x) p2 + t - q), i.e. theta(x) = theta0 + J x with
+//   theta0 = [R_c rows, 0 after each row, 1],
+//   d theta / d alpha_k = [e_k x (columns of R_c), (e_k x c_f)],   d theta / d t_k = e_k in slot 4a+3,
+// so A^T A = J^T M J and A^T l = -J^T M theta0.  The centring only conditions the sums; x is the
+// reference's x.  Returns x in s.delta and the pivot check in s.spd (warp 0 of block 0).
+__device__ void lin_solve(Shared& s, const Rigid& Tc, const double* cf, int lane) {
+  for (int e = lane; e < 13 * 6; e += 32) {
+    const int r = e / 6, k = e % 6;
+    double v = 0.0;
+    if (r < 12) {
+      const int a = r / 4, b = r % 4;
+      if (k < 3) {
+        if (a != k) {
+          const bool neg = (a == (k + 1) % 3);
+          const int c = neg ? (k + 2) % 3 : (k + 1) % 3;  // e_k x v: component a takes -/+ v[c]
+          const double vc = (b < 3) ? Tc.r[c * 3 + b] : cf[c];
+          v = neg ? -vc : vc;
+        }
+      } else if (b == 3 && k - 3 == a) {
+        v = 1.0;
+      }
+    }
+    s.J[r][k] = v;
+  }
+  if (lane < 13) {
+    const int a = lane / 4, b = lane % 4;
+    s.th[lane] = (lane == 12) ? 1.0 : ((b < 3) ? Tc.r[a * 3 + b] : 0.0);
+  }
+  __syncwarp();
+  moment_products(s, lane);
+  int ri, cj;
+  tri_coords(lane, ri, cj);
+  double val = 1.0;
+  if (ri < 6) val = s.A[ri * 6 + cj];
+  else if (cj < 6) val = -s.g[cj];
+  double inv[6];
+  const bool spd = warp_chol7_factor(val, ri, cj, inv);
+  const double sol = warp_chol7_backsolve(val, lane, ri, cj, inv);
+  if (lane < 6) s.delta[lane] = sol;
+  if (lane == 0) s.spd = spd ? 1 : 0;
+  __syncwarp();
+}
+
 // sigma of the free parameters: Cxx = s0^2 (A^T P A)^-1 in the reference's formulation
 // (optimization.py:147-160): N = w * sum a a^T + diag(w_obs), vPv = w sum r^2 + sum w_obs dx^2.
 // Called by a full warp: lane j < 6 produces sigma[j] (one column of the inverse each).
@@ -820,7 +871,7 @@ __device__ bool predicted_median_mad(Shared& s, const RSArgs& a, RSWork wk, cons
   unsigned long long* cand_med = wk.cand;
   unsigned long long* cand_edge = wk.cand + RS_CAP;
   for (long long i = blockIdx.x * (long long)RS_THREADS + tid; i < a.K; i += (long long)gridDim.x * RS_THREADS) {
-    if ((double)a.q_nrm[i].w >= a.min_planarity) {
+    if ((double)a.q_nrm[i].w >= a.stat_minpl) {
       const double d = a.dist[i];
       const int b = lh_bin(d, pm, pd);
       if (b < LH_BINS) {
@@ -843,13 +894,13 @@ __device__ bool predicted_median_mad(Shared& s, const RSArgs& a, RSWork wk, cons
   for (int t = tid; t < (int)cnt_med; t += RS_THREADS) s.sortbuf[t] = cand_med[t];
   __syncthreads();
   block_select(s, s.sortbuf, (int)cnt_med, kA, 64, ~0ull, klo, khi);
-  median = even ? 0.5 * (key_to_f64(klo) + key_to_f64(khi)) : key_to_f64(klo);
+  median = even ? (a.variant ? key_to_f64(khi) : 0.5 * (key_to_f64(klo) + key_to_f64(khi))) : key_to_f64(klo);
   __syncthreads();
   for (int t = tid; t < (int)cnt_edge; t += RS_THREADS)
     s.sortbuf[t] = f64_to_key(fabs(__longlong_as_double((long long)cand_edge[t]) - median));
   __syncthreads();
   block_select(s, s.sortbuf, (int)cnt_edge, kM, 64, ~0ull, klo, khi);
-  mad = even ? 0.5 * (key_to_f64(klo) + key_to_f64(khi)) : key_to_f64(klo);
+  mad = even ? (a.variant ? key_to_f64(khi) : 0.5 * (key_to_f64(klo) + key_to_f64(khi))) : key_to_f64(klo);
   __syncthreads();
   return true;
 }
@@ -883,19 +934,19 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
   unsigned int n1 = 0;
   double median = 0.0, mad = 0.0;
   bool fast = false;
-  if (a.hist_expected && st->pred_valid && st->pred_minpl == a.min_planarity && st->pred_mad > 0.0)
+  if (a.hist_expected && st->pred_valid && st->pred_minpl == a.stat_minpl && st->pred_mad > 0.0)
     fast = predicted_median_mad<MULTI>(s, a, wk, st, n1, median, mad);
   sicp_iter_record* rec = a.rec;
   if (!fast) {
     __syncthreads();
     radix_median<MULTI, 0>(s, a, wk, 0.0, n1);
     if (n1 != 0) {
-      median = 0.5 * (s.bc[0] + s.bc[1]);
+      median = a.variant ? s.bc[1] : 0.5 * (s.bc[0] + s.bc[1]);
       __syncthreads();
       RS_STAMP(1);
       unsigned int n1b = 0;
       radix_median<MULTI, 1>(s, a, wk, median, n1b);
-      mad = 0.5 * (s.bc[0] + s.bc[1]);
+      mad = a.variant ? s.bc[1] : 0.5 * (s.bc[0] + s.bc[1]);
     }
   }
   if (n1 == 0) {
@@ -907,7 +958,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     }
     return;
   }
-  const double lim = 3.0 * mad;
+  // python: |d - med| <= 3 mad (corrpts.py:176-188); linearised: not > 3 (1.4826 mad) (corrpts.cpp:61-66)
+  const double lim = a.variant ? 3.0 * (1.4826 * mad) : 3.0 * mad;
   __syncthreads();
   if (fast) RS_STAMP(1);
   RS_STAMP(2);
@@ -1064,8 +1116,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       const double sum_d = s.tot[1 * RS_NACC + 24], sum_d2 = s.tot[1 * RS_NACC + 25];
       const double mean_d = (n_kept > 0) ? sum_d / (double)n_kept : nan("");
       const double var_d = (n_kept > 0) ? fmax(sum_d2 / (double)n_kept - mean_d * mean_d, 0.0) : nan("");
+      // the C++ driver prints the SAMPLE std of the kept distances as its "orig:0" row (simpleicp.cpp:95-100)
+      const double var_d1 = (n_kept > 1) ? fmax(sum_d2 - (double)n_kept * mean_d * mean_d, 0.0) / (double)(n_kept - 1) : nan("");
       double w = st->w;
-      if (a.it == 0 || !(w > 0.0)) {
+      if (a.variant) {
+        w = 1.0;
+      } else if (a.it == 0 || !(w > 0.0)) {
         w = a.w_param;
         if (!(w > 0.0)) w = 1.0 / var_d;  // distance_weights=None: 1/std(d)^2 (simpleicp.py:233-234)
       }
@@ -1073,7 +1129,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       LmOut lo;
       lo.iters = 0;
       lo.ok = 1;
-      if (!skip) {
+      if (!skip && a.variant) {
+        lin_solve(s, st->T, cf, lane);
+        lo.iters = 1;
+        lo.ok = s.spd;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) lo.x[j] = s.delta[j];
+      } else if (!skip) {
         lm_solve(s, a, w, st->x, cm, cf, lo, lane);
         if (lane == 0) {
           wk.phase_t[19] = global_timer_ns();
@@ -1087,10 +1149,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
         rec->mad = mad;
         st->pred_med = median;
         st->pred_mad = mad;
-        st->pred_minpl = a.min_planarity;
+        st->pred_minpl = a.stat_minpl;
         st->pred_valid = (mad > 0.0 && isfinite(mad) && isfinite(median)) ? 1 : 0;
         rec->mean_dist = mean_d;
-        rec->std_dist = sqrt(var_d);
+        rec->std_dist = sqrt(a.variant ? var_d1 : var_d);
         rec->distance_weight = w;
         rec->lm_iterations = lo.iters;
         rec->n_bruteforce = a.unresolved ? (int)a.unresolved[K] : 0;
@@ -1101,7 +1163,22 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
         if (!skip) {
           for (int j = 0; j < 6; ++j) st->x_new[j] = lo.x[j];
           for (int e = 0; e < 36; ++e) st->An[e] = s.Ak[e];
-          st->T_new = rigid_from_x(lo.x);
+          if (a.variant) {
+            // cloud <- dH cloud (pointcloud.cpp:149-152), residuals of the linear model
+            const Rigid dH = rigid_from_x(lo.x);
+            st->T_new = rigid_compose(dH, Tin);
+            Rigid L;  // I + [alpha]x, t
+            L.r[0] = 1.0; L.r[1] = -lo.x[2]; L.r[2] = lo.x[1];
+            L.r[3] = lo.x[2]; L.r[4] = 1.0; L.r[5] = -lo.x[0];
+            L.r[6] = -lo.x[1]; L.r[7] = lo.x[0]; L.r[8] = 1.0;
+            L.t[0] = lo.x[3]; L.t[1] = lo.x[4]; L.t[2] = lo.x[5];
+            st->T_res = rigid_compose(L, Tin);
+            const Rigid Hr = st->H_rep;
+            st->H_rep = (a.variant == SICP_VARIANT_LINEARIZED_CPP) ? rigid_compose(Hr, dH) : rigid_compose(dH, Hr);
+          } else {
+            st->T_new = rigid_from_x(lo.x);
+            st->T_res = st->T_new;
+          }
           st->lm_ok = lo.ok;
         }
       }
@@ -1114,7 +1191,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
 
   // ---- E: residuals at the solution, in the reference's operation order
   {
-    const Rigid Tn = st->T_new;
+    const Rigid Tn = st->T_res;
     double sr = 0.0, sr2 = 0.0;
     for (long long i = blockIdx.x * (long long)RS_THREADS + tid; i < K; i += (long long)G * RS_THREADS) {
       if (!a.keep[i]) continue;
@@ -1177,18 +1254,28 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     }
     const long long n = st->n_kept;
     const double mean = t0 / (double)n;
-    const double sd = sqrt(fmax(t1 / (double)n - mean * mean, 0.0));
+    // population std (numpy default, simpleicp.py:263) / sample std (c++/src/simpleicp.cpp:184-188)
+    const double sd = a.variant ? sqrt(fmax(t1 - (double)n * mean * mean, 0.0) / (double)(n - 1))
+                                : sqrt(fmax(t1 / (double)n - mean * mean, 0.0));
     // one lane per parameter: sigma_j, and the new cumulative parameters
-    uncertainties(s, a, st->An, st->w, st->x_new, t1, n, lane, st->sigma);
-    if (lane < 6) {
-      rec->x[lane] = st->x_new[lane];
-      st->x[lane] = st->x_new[lane];
+    if (a.variant) {
+      if (lane < 6) {
+        st->sigma[lane] = nan("");
+        rec->x[lane] = st->x_new[lane];  // the increments of this iteration
+      }
+    } else {
+      uncertainties(s, a, st->An, st->w, st->x_new, t1, n, lane, st->sigma);
+      if (lane < 6) {
+        rec->x[lane] = st->x_new[lane];
+        st->x[lane] = st->x_new[lane];
+      }
     }
     if (lane == 0) {
       rec->mean_res = mean;
       rec->std_res = sd;
       st->T = st->T_new;
       st->Tinv = rigid_inverse(st->T_new);
+      if (!a.variant) st->H_rep = st->T_new;
       // stop rule (simpleicp.py:355-379): relative change in percent of mean and population std
       int stop = 0;
       if (a.it > 0) {
@@ -1304,6 +1391,8 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
   a.state = c.dev_state.p;
   a.rec = c.ws.rec.p + rec_slot;
   a.min_planarity = p.min_planarity;
+  a.variant = c.variant;
+  a.stat_minpl = c.variant ? -kInf : p.min_planarity;
   a.min_change = p.min_change;
   a.w_param = p.lsq.distance_weight;
   for (int j = 0; j < 6; ++j) {

@@ -31,6 +31,12 @@ struct DevState {
   double pred_med, pred_mad, pred_minpl;
   int pred_valid;   // pred_* describe a finished reject phase of this run
   int hist_filled;  // the last match filled the linear histogram with the current pred_*
+  // Linearised variant (SICP_VARIANT_LINEARIZED*): T_res is the affine map (I + [alpha]x) T + t
+  // whose point-to-plane residuals are the reference's "A x - l" (c++/src/corrpts.cpp:155);
+  // H_rep is the matrix the reference driver reports (dH * H, or H * dH for the C++ driver).
+  // In the default variant T_res == T_new and H_rep == T.
+  Rigid T_res;
+  Rigid H_rep;
 };
 
 // Linear histogram shared by the match kernels (producers) and k_reject_solve (consumer).
@@ -69,6 +75,8 @@ struct RSArgs {
   int do_solve;
   int arm_stop;
   int hist_expected;  // the preceding match launch fed lin_hist (if the predictor was valid)
+  int variant;        // sicp_variant
+  double stat_minpl;  // planarity bound of the set the median/MAD are taken over (-inf: everybody)
 };
 
 struct RSWork {
