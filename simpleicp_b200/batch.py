@@ -70,6 +70,32 @@ def tile_slabs(X_fix: np.ndarray, X_mov: np.ndarray, n_slabs: int, overlap: floa
     return out
 
 
+# Engines (one CUDA stream + one libsicp_b200 context each) are kept between calls: creating a
+# context and growing its device buffers costs far more than one small registration.
+_ENGINES: dict = {}
+
+
+def _engine_pool(device: int, n: int):
+    import torch
+
+    from . import _capi
+
+    pool = _ENGINES.setdefault(int(device), [])
+    with torch.cuda.device(device):
+        while len(pool) < n:
+            stream = torch.cuda.Stream(device=device)
+            pool.append((stream, _capi.Engine(device, stream=int(stream.cuda_stream))))
+    return pool
+
+
+def close_engine_pool() -> None:
+    """Release the engines simpleicp_batch keeps between calls."""
+    for pool in _ENGINES.values():
+        for _, eng in pool:
+            eng.close()
+    _ENGINES.clear()
+
+
 def simpleicp_batch(
     pairs: Sequence[Tuple[np.ndarray, np.ndarray]] | Callable[[int], Tuple[np.ndarray, np.ndarray]],
     n_pairs: Optional[int] = None,
@@ -110,23 +136,24 @@ def simpleicp_batch(
 
         import torch
 
-        from . import _capi
         from .simpleicp import register
 
         n_workers = max(1, min(concurrency, len(mine)))
         errors = []
+        pool = _engine_pool(device, n_workers)
+        todo, lock = iter(range(len(mine))), threading.Lock()
 
         def worker(w):
             try:
                 with torch.cuda.device(device):
-                    stream = torch.cuda.Stream(device=device)
-                    eng = _capi.Engine(device, stream=int(stream.cuda_stream))
-                    try:
-                        for j in range(w, len(mine), n_workers):
-                            Xf, Xm = get(mine[j])
-                            local[j] = record(register(Xf, Xm, engine=eng, **run_kwargs))
-                    finally:
-                        eng.close()
+                    _, eng = pool[w]
+                    while True:
+                        with lock:  # dynamic hand-out: iteration counts (3 .. max_iterations) vary a lot
+                            j = next(todo, None)
+                        if j is None:
+                            break
+                        Xf, Xm = get(mine[j])
+                        local[j] = record(register(Xf, Xm, engine=eng, **run_kwargs))
             except Exception as e:  # surfaced after the join
                 errors.append(e)
 

@@ -1,5 +1,8 @@
 // capi.cu — the extern "C" boundary declared in include/sicp_b200.h.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -554,8 +557,16 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
       SICP_REQUIRE(p->lsq.obs_weight[j] == 0.0, SICP_ERR_BAD_ARG,
                    "the linearised variants have no observed or fixed parameters: "
                    "rbp_observation_weights must be all zero");
+  static const bool trace = std::getenv("SICP_TRACE_RUN") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto tr = [&](const char* what, int it) {
+    if (trace)
+      fprintf(stderr, "[sicp_run] %-12s it=%d t=%.1f us\n", what, it,
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count());
+  };
   init_state(c, p->lsq.x0, nullptr, true);
   std::memset(out, 0, sizeof(*out));
+  tr("init", -1);
 
   cudaEvent_t e0, e1;
   SICP_CUDA(cudaEventCreate(&e0));
@@ -571,12 +582,15 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
   c.expect_unresolved = true;
   for (int it = 0; it < p->max_iterations; ++it) {
     match_launch(c, true, nullptr, nullptr, c.expect_unresolved);
+    tr("match", it);
     reject_solve_launch(c, *p, it, true, true, it);
+    tr("rs", it);
     if (it >= next_sync || it + 1 == p->max_iterations) {
       next_sync = (it < 2) ? it + 1 : it + every;
       fetch_records(c, fetched, it + 1 - fetched);
       SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
       sync(c);
+      tr("synced", it);
       fetched = it + 1;
       done = h.iterations_done;
       c.expect_unresolved = c.rec_host[it].n_bruteforce > 0;
@@ -600,6 +614,7 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
   compact_residuals_launch(c);
   SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
   sync(c);
+  tr("final", -1);
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0);
