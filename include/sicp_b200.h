@@ -191,6 +191,33 @@ int32_t sicp_get_residuals(sicp_ctx* ctx, double* residuals /*[h|d] cap*/, int64
 int32_t sicp_iterate(sicp_ctx* ctx, const sicp_run_params* p, const double x_in[6],
                      sicp_iter_record* rec /*[h] or NULL: fully asynchronous*/);
 
+/* PointCloud.select_n_points (pointcloud.py:121-147) applied to the CURRENT selection on the
+ * device: keeps the points at rint(linspace(0, m-1, n)) (numpy arithmetic; the linearised
+ * variants round half away from zero as c++/src/pointcloud.cpp:92-96 does); no-op when n >= m.
+ * idx_out (may be NULL) receives the resulting selection, sicp_set_selected's K is updated.     */
+int32_t sicp_select_n_points(sicp_ctx* ctx, int64_t n, int64_t* idx_out /*[h|d] min(n, m) or NULL*/);
+
+/* ---- SimpleICP.run as ONE call (simpleicp.py:75-324) --------------------------------------------
+ * add_point_clouds + [select_in_range] + select_n_points + estimate_normals + the iteration loop
+ * + the final transform_by_H, scheduled so that the host->device transfer of the movable cloud
+ * overlaps the fixed-side work (grid, subsample, normals).  Equivalent to sicp_set_clouds,
+ * sicp_set_selected(NULL), [sicp_select_in_range], sicp_select_n_points, sicp_estimate_normals,
+ * sicp_run, sicp_transform in sequence; every stage-by-stage call remains valid afterwards
+ * (sicp_get_residuals, sicp_get_knn, sicp_match ...).                                            */
+typedef struct {
+  int64_t correspondences;       /* simpleicp.py:78 (default 1000)                                */
+  int32_t neighbors;             /* simpleicp.py:79 (default 10)                                  */
+  int32_t reserved;
+  double max_overlap_distance;   /* <= 0 or +inf: clouds fully overlap (simpleicp.py:81)          */
+  sicp_run_params run;
+} sicp_register_params;
+int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz /*[h|d] n_fix x 3*/, int64_t n_fix,
+                      const double* mov_xyz /*[h|d] n_mov x 3*/, int64_t n_mov,
+                      const sicp_register_params* p, sicp_run_result* out /*[h]*/,
+                      sicp_iter_record* log /*[h] max_iterations entries or NULL*/,
+                      double* mov_xyz_out /*[h|d] n_mov x 3 or NULL*/,
+                      int64_t* n_selected /*[h] or NULL*/);
+
 /* ---- PointCloud.transform_by_H (pointcloud.py:205-217), final application simpleicp.py:316 -- */
 int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out /*[h|d] n_mov x 3*/);
 

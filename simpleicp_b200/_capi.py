@@ -26,6 +26,7 @@ SYMBOLS = (
     "sicp_set_clouds", "sicp_set_selected", "sicp_select_in_range", "sicp_estimate_normals",
     "sicp_set_normals", "sicp_get_knn", "sicp_match", "sicp_reject", "sicp_solve",
     "sicp_uncertainties", "sicp_run", "sicp_get_transform", "sicp_get_residuals", "sicp_iterate", "sicp_transform",
+    "sicp_select_n_points", "sicp_register",
     "sicp_get_timings", "sicp_time_stages", "sicp_get_phase_times",
     "sicp_xyz_load", "sicp_xyz_free", "sicp_xyz_save", "sicp_io_last_error",
 )
@@ -39,6 +40,11 @@ class LsqParams(C.Structure):
 class RunParams(C.Structure):
     _fields_ = [("min_planarity", C.c_double), ("min_change", C.c_double),
                 ("max_iterations", C.c_int32), ("reserved", C.c_int32), ("lsq", LsqParams)]
+
+
+class RegisterParams(C.Structure):
+    _fields_ = [("correspondences", C.c_int64), ("neighbors", C.c_int32), ("reserved", C.c_int32),
+                ("max_overlap_distance", C.c_double), ("run", RunParams)]
 
 
 class IterRecord(C.Structure):
@@ -75,13 +81,20 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    override = os.environ.get("SICP_B200_LIB")  # diagnostics: an experimental build of the same ABI
+    if override:
+        lib_path = Path(override)
+        if not lib_path.exists():
+            raise ImportError(f"SICP_B200_LIB={override} does not exist")
+    else:
+        lib_path = LIB_PATH
+    if not override and not LIB_PATH.exists():
         if not build_if_missing:
             raise ImportError(f"{LIB_PATH} is missing; run `python -m simpleicp_b200._build`")
         from . import _build
 
         _build.build()
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(lib_path))
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.sicp_abi_version.restype = i32
     lib.sicp_last_error.restype = C.c_char_p
@@ -106,6 +119,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "sicp_get_residuals": [vp, vp, i64, C.POINTER(i64)],
         "sicp_iterate": [vp, C.POINTER(RunParams), C.POINTER(dbl), C.POINTER(IterRecord)],
         "sicp_transform": [vp, C.POINTER(dbl), vp],
+        "sicp_select_n_points": [vp, i64, vp],
+        "sicp_register": [vp, vp, i64, vp, i64, C.POINTER(RegisterParams), C.POINTER(RunResult),
+                          C.POINTER(IterRecord), vp, C.POINTER(i64)],
         "sicp_get_timings": [vp, C.POINTER(Timings)],
         "sicp_time_stages": [vp, C.POINTER(RunParams), i32, i32, C.POINTER(dbl)],
         "sicp_get_phase_times": [vp, C.POINTER(dbl)],
@@ -352,6 +368,38 @@ class Engine:
         res = np.empty(int(out.n_residuals), dtype=np.float64)
         self._check(self._lib.sicp_get_residuals(self._h, _ptr(res), res.size, C.byref(n)))
         return out, [log[i] for i in range(out.iterations)], res
+
+    def select_n_points(self, n: int, want_idx: bool = True):
+        """PointCloud.select_n_points on the device; returns the resulting selection (int64)."""
+        k = min(int(n), self.K if self.K else self.n_fix)
+        idx = np.empty(k, dtype=np.int64) if want_idx else None
+        self._check(self._lib.sicp_select_n_points(self._h, int(n), None if idx is None else _ptr(idx)))
+        self.K = k
+        return idx
+
+    def register_fused(self, X_fix, X_mov, correspondences, neighbors, max_overlap_distance,
+                       params: RunParams, transform_out=None):
+        """SimpleICP.run as one library call (sicp_register): uploads, selection, normals, the
+        loop and the final transform, with the movable upload overlapped with the fixed-side work."""
+        Xf, Xm = _as_f64_xyz(X_fix), _as_f64_xyz(X_mov)
+        self.n_fix, self.n_mov = int(Xf.shape[0]), int(Xm.shape[0])
+        rp = RegisterParams()
+        rp.correspondences = int(correspondences)
+        rp.neighbors = int(neighbors)
+        rp.max_overlap_distance = float(max_overlap_distance)
+        rp.run = params
+        out = RunResult()
+        log = (IterRecord * int(params.max_iterations))()
+        if transform_out is None:
+            transform_out = pinned_empty((self.n_mov, 3), np.float64)
+        nsel = C.c_int64(0)
+        self._check(self._lib.sicp_register(self._h, _ptr(Xf), self.n_fix, _ptr(Xm), self.n_mov, C.byref(rp),
+                                            C.byref(out), log, _ptr(transform_out), C.byref(nsel)))
+        self.K = int(nsel.value)
+        n = C.c_int64(0)
+        res = np.empty(int(out.n_residuals), dtype=np.float64)
+        self._check(self._lib.sicp_get_residuals(self._h, _ptr(res), res.size, C.byref(n)))
+        return out, [log[i] for i in range(out.iterations)], res, transform_out
 
     def get_transform(self) -> np.ndarray:
         """The 4 x 4 transform the last run/solve applied to the movable cloud."""

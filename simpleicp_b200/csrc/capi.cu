@@ -38,6 +38,19 @@ __global__ void k_iota(long long* p, long long n) {
   if (i < n) p[i] = i;
 }
 
+// PointCloud.select_n_points (pointcloud.py:121-147): sel[i] = src[rint(linspace(0, m-1, n)[i])],
+// numpy's linspace arithmetic (i * step, last element forced to m-1), rint = round-half-even.
+// away = 1 gives the native drivers' C round() (c++/src/pointcloud.cpp:92-96).  src == NULL: iota.
+__global__ void k_select_n(const long long* __restrict__ src, long long m, long long n, int away,
+                           long long* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double step = (n > 1) ? (double)(m - 1) / (double)(n - 1) : 0.0;
+  const double y = (i == n - 1 && n > 1) ? (double)(m - 1) : (double)i * step;
+  const long long j = (long long)(away ? round(y) : rint(y));
+  out[i] = src ? src[j] : j;
+}
+
 __global__ void k_check_sel(const long long* __restrict__ sel, long long K, long long n,
                             unsigned int* __restrict__ bad) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -537,9 +550,10 @@ int32_t sicp_iterate(sicp_ctx* ctx, const sicp_run_params* p, const double x_in[
   API_END
 }
 
-int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
-                 sicp_iter_record* log) {
-  API_BEGIN(ctx)
+// The iteration loop of SimpleICP.run (simpleicp.py:184-281); shared by sicp_run and sicp_register.
+static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_result* out,
+                     sicp_iter_record* log) {
+  (void)ctx;
   require_normals(c);
   SICP_REQUIRE(p && out, SICP_ERR_BAD_ARG, "NULL argument");
   SICP_REQUIRE(p->max_iterations >= 1 && p->max_iterations <= kMaxRecords, SICP_ERR_BAD_ARG,
@@ -639,6 +653,12 @@ int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
   c.tm.reject_solve_ms = ms;
   if (log) std::memcpy(log, c.rec_host, sizeof(sicp_iter_record) * done);
   c.matched = c.rejected = c.solved = true;
+}
+
+int32_t sicp_run(sicp_ctx* ctx, const sicp_run_params* p, sicp_run_result* out,
+                 sicp_iter_record* log) {
+  API_BEGIN(ctx)
+  run_loop(ctx, c, p, out, log);
   API_END
 }
 
@@ -663,11 +683,7 @@ int32_t sicp_get_residuals(sicp_ctx* ctx, double* residuals, int64_t cap, int64_
   API_END
 }
 
-int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out) {
-  API_BEGIN(ctx)
-  require_clouds(c);
-  SICP_REQUIRE(H && mov_xyz_out, SICP_ERR_BAD_ARG, "NULL argument");
-  const Rigid T = rigid_from_H(H);
+static void transform_to(Ctx& c, const Rigid& T, double* mov_xyz_out) {
   StageTimer t(c, &c.tm.transform_ms);
   if (is_device_ptr(mov_xyz_out)) {
     transform_launch(c, T, c.mov_xyz.p, mov_xyz_out, c.n_mov);
@@ -678,6 +694,169 @@ int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out) {
     copy_any(c, mov_xyz_out, s, sizeof(double) * 3 * c.n_mov);
   }
   t.stop();
+}
+
+int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out) {
+  API_BEGIN(ctx)
+  require_clouds(c);
+  SICP_REQUIRE(H && mov_xyz_out, SICP_ERR_BAD_ARG, "NULL argument");
+  transform_to(c, rigid_from_H(H), mov_xyz_out);
+  API_END
+}
+
+int32_t sicp_select_n_points(sicp_ctx* ctx, int64_t n, int64_t* idx_out) {
+  API_BEGIN(ctx)
+  require_selected(c);
+  SICP_REQUIRE(n >= 1, SICP_ERR_BAD_ARG, "n must be >= 1");
+  if (n < c.K) {
+    // pointcloud.py:137-147: only when fewer points are asked for than are selected
+    c.sel_tmp.reserve(n);
+    k_select_n<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(c.sel_idx.p, c.K, n, c.variant != SICP_VARIANT_PYTHON,
+                                                                  c.sel_tmp.p);
+    c.sel_idx.reserve(n);
+    SICP_CUDA(cudaMemcpyAsync(c.sel_idx.p, c.sel_tmp.p, sizeof(long long) * n, cudaMemcpyDeviceToDevice, c.stream));
+    c.K = n;
+    gather_queries_launch(c);
+    c.have_normals = false;
+    c.matched = c.rejected = c.solved = false;
+  }
+  if (idx_out) copy_any(c, idx_out, c.sel_idx.p, sizeof(long long) * c.K);
+  sync(c);
+  API_END
+}
+
+int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, const double* mov_xyz,
+                      int64_t n_mov, const sicp_register_params* rp, sicp_run_result* out,
+                      sicp_iter_record* log, double* mov_xyz_out, int64_t* n_selected) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(fix_xyz && mov_xyz && rp && out, SICP_ERR_BAD_ARG, "NULL argument");
+  SICP_REQUIRE(n_fix > 0 && n_mov > 0, SICP_ERR_BAD_ARG, "clouds must not be empty");
+  SICP_REQUIRE(n_fix < (1ll << 31) && n_mov < (1ll << 31), SICP_ERR_BAD_ARG,
+               "clouds are limited to 2^31 - 1 points");
+  SICP_REQUIRE(rp->correspondences >= 1, SICP_ERR_BAD_ARG, "correspondences must be >= 1");
+  const bool overlap = rp->max_overlap_distance > 0 && std::isfinite(rp->max_overlap_distance);
+  static const bool trace = std::getenv("SICP_TRACE_RUN") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto tr = [&](const char* what) {
+    if (trace)
+      fprintf(stderr, "[sicp_register] %-14s t=%.1f us\n", what,
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count());
+  };
+  c.fix_xyz.reserve(3 * n_fix);
+  c.mov_xyz.reserve(3 * n_mov);
+  c.n_fix = n_fix;
+  c.n_mov = n_mov;
+  c.gfix.built = false;
+  c.K = 0;
+  c.have_normals = false;
+  c.matched = c.rejected = c.solved = false;
+  // Transfers in the order the pipeline consumes them.  The fixed cloud goes first on the
+  // context's stream; the movable cloud follows on the copy stream, and while it crosses PCIe the
+  // fixed-side work (subsample, k-NN + PCA normals) runs.  With the overlap filter the selection
+  // itself needs the movable grid, so there the order is mov, fix as in sicp_set_clouds.
+  // The second transfer is queued only AFTER the first cloud's grid build: that build reads a few
+  // bytes back (bounding box, occupancy) and every device->host transaction issued while the
+  // 24 MB host->device copy is in flight was measured to complete only when the copy ends
+  // (bbox read-back 0.46 ms instead of 0.03 ms, whether by memcpy or by a store to mapped memory).
+  {
+    StageTimer t(c, &c.tm.upload_ms);
+    copy_any(c, overlap ? c.mov_xyz.p : c.fix_xyz.p, overlap ? mov_xyz : fix_xyz,
+             sizeof(double) * 3 * (overlap ? n_mov : n_fix));
+    t.stop();
+  }
+  auto queue_second_copy = [&]() {
+    SICP_CUDA(cudaEventRecord(c.ev_user, c.stream));
+    SICP_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_user, 0));
+    SICP_CUDA(cudaMemcpyAsync(overlap ? c.fix_xyz.p : c.mov_xyz.p, overlap ? fix_xyz : mov_xyz,
+                              sizeof(double) * 3 * (overlap ? n_fix : n_mov), cudaMemcpyDefault, c.copy_stream));
+    SICP_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
+    tr("2nd copy queued");
+  };
+  auto build_mov = [&]() {
+    StageTimer t(c, &c.tm.grid_mov_ms);
+    grid_build(c, c.gmov, c.mov_xyz.p, n_mov);
+    make_float4_copy(c);
+    t.stop();
+  };
+  auto build_fix = [&]() {
+    StageTimer t(c, &c.tm.grid_fix_ms);
+    grid_build(c, c.gfix, c.fix_xyz.p, n_fix);
+    t.stop();
+  };
+  c.sel_idx.reserve(n_fix);
+  c.tm.overlap_ms = 0;
+  if (overlap) {
+    build_mov();
+    queue_second_copy();
+    SICP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+    // PointCloud.select_in_range on all fixed points (simpleicp.py:160-170), compacted on the host
+    k_iota<<<(unsigned)((n_fix + 255) / 256), 256, 0, c.stream>>>(c.sel_idx.p, n_fix);
+    c.K = n_fix;
+    gather_queries_launch(c);
+    Rigid T0 = rigid_from_x(rp->run.lsq.x0);
+    init_state(c, nullptr, &T0, true);
+    StageTimer t(c, &c.tm.overlap_ms);
+    c.dist.reserve(c.K);
+    c.keep.reserve(c.K);
+    match_launch(c, false, c.dist.p);
+    SICP_CUDA(cudaMemsetAsync(c.misc_counters.p + 8, 0, sizeof(unsigned int), c.stream));
+    k_range_keep<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(
+        c.dist.p, c.K, rp->max_overlap_distance * rp->max_overlap_distance, c.keep.p, c.misc_counters.p + 8);
+    std::vector<uint8_t> keep((size_t)n_fix);
+    copy_any(c, keep.data(), c.keep.p, (size_t)n_fix);
+    t.stop();
+    std::vector<long long> idx;
+    idx.reserve((size_t)n_fix);
+    for (long long i = 0; i < n_fix; ++i)
+      if (keep[(size_t)i]) idx.push_back(i);
+    SICP_REQUIRE(!idx.empty(), SICP_ERR_NO_OVERLAP, "Point clouds do not overlap within max_overlap_distance");
+    copy_any(c, c.sel_idx.p, idx.data(), sizeof(long long) * idx.size());
+    sync(c);  // idx is a local
+    c.K = (long long)idx.size();
+    build_fix();
+  } else {
+    build_fix();
+    queue_second_copy();
+    if (rp->correspondences < n_fix) {
+      k_select_n<<<(unsigned)((rp->correspondences + 255) / 256), 256, 0, c.stream>>>(
+          nullptr, n_fix, rp->correspondences, c.variant != SICP_VARIANT_PYTHON, c.sel_idx.p);
+      c.K = rp->correspondences;
+    } else {
+      k_iota<<<(unsigned)((n_fix + 255) / 256), 256, 0, c.stream>>>(c.sel_idx.p, n_fix);
+      c.K = n_fix;
+    }
+  }
+  if (rp->correspondences < c.K) {
+    c.sel_tmp.reserve(rp->correspondences);
+    k_select_n<<<(unsigned)((rp->correspondences + 255) / 256), 256, 0, c.stream>>>(
+        c.sel_idx.p, c.K, rp->correspondences, c.variant != SICP_VARIANT_PYTHON, c.sel_tmp.p);
+    SICP_CUDA(cudaMemcpyAsync(c.sel_idx.p, c.sel_tmp.p, sizeof(long long) * rp->correspondences,
+                              cudaMemcpyDeviceToDevice, c.stream));
+    c.K = rp->correspondences;
+  }
+  tr("fix grid+select");
+  gather_queries_launch(c);
+  {
+    StageTimer t(c, &c.tm.normals_ms);
+    estimate_normals_launch(c, rp->neighbors);
+    c.have_normals = true;
+    t.stop();
+  }
+  tr("normals");
+  if (!overlap) {
+    SICP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+    build_mov();
+  }
+  tr("mov grid");
+  if (n_selected) *n_selected = c.K;
+  run_loop(ctx, c, &rp->run, out, log);
+  tr("loop");
+  if (mov_xyz_out) {
+    transform_to(c, rigid_from_H(c.last_T), mov_xyz_out);
+  }
+  SICP_CUDA(cudaStreamSynchronize(c.copy_stream));
+  sync(c);
+  tr("transform+d2h");
   API_END
 }
 

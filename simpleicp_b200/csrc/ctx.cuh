@@ -75,6 +75,7 @@ struct Ctx {
   // selection (ascending fixed-cloud indices) and per-query data
   long long K = 0;
   DevBuf<long long> sel_idx;
+  DevBuf<long long> sel_tmp;
   DevBuf<double> q_xyz;   // K x 3 gathered fixed points
   DevBuf<float4> q_nrm;   // (nx, ny, nz, planarity) float32 as the reference stores them
   bool have_normals = false;

@@ -9,6 +9,10 @@
 //   k_scatter     : cell-sorted 32-byte records     (reads 28 n B, writes 32 n B)
 #include <algorithm>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "ctx.cuh"
 
 namespace sicp {
@@ -264,6 +268,13 @@ void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
   cudaStream_t st = c.stream;
   g.built = false;
   g.n = n;
+  static const bool trace = std::getenv("SICP_TRACE_RUN") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto tr = [&](const char* what) {
+    if (trace)
+      fprintf(stderr, "[grid_build] %-12s t=%.1f us\n", what,
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count());
+  };
   // ---- bounding box
   c.bbox_keys.reserve(16);
   c.ws.scal.reserve(256);
@@ -272,7 +283,9 @@ void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
   k_bbox<<<std::max(nb, 1), 256, 0, st>>>(xyz, n, c.bbox_keys.p);
   k_bbox_decode<<<1, 32, 0, st>>>(c.bbox_keys.p, c.ws.scal.p);
   SICP_CUDA(cudaMemcpyAsync(c.scal_host, c.ws.scal.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  tr("bbox queued");
   SICP_CUDA(cudaStreamSynchronize(st));
+  tr("bbox synced");
   double lo[3], ext[3];
   for (int a = 0; a < 3; ++a) {
     lo[a] = c.scal_host[a];
@@ -318,9 +331,12 @@ void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
     k_scan_down<<<(unsigned)nsb, 256, 0, st>>>(g.fill.p, g.n_cells, g.block_sums.p, g.cell_start.p);
     k_scan_total<<<1, 32, 0, st>>>(g.fill.p, g.n_cells, g.cell_start.p);
     c.tm.kernel_launches += 5;
-    unsigned int nocc = 0;
-    SICP_CUDA(cudaMemcpyAsync(&nocc, c.misc_counters.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    unsigned int* nocc_host = reinterpret_cast<unsigned int*>(c.scal_host + 16);
+    SICP_CUDA(cudaMemcpyAsync(nocc_host, c.misc_counters.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    tr("count queued");
     SICP_CUDA(cudaStreamSynchronize(st));
+    tr("count synced");
+    const unsigned int nocc = *nocc_host;
     g.n_occupied = nocc;
     double occ = (double)n / (double)std::max<unsigned int>(nocc, 1u);
     // accept when within a factor 1.6 of the target, or when the cell cap binds
@@ -341,6 +357,7 @@ void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
     k_sort_cells<<<(unsigned)((g.n_cells + 255) / 256), 256, 0, st>>>(g.cell_start.p, g.n_cells,
                                                                      g.recs.p);
   SICP_CUDA(cudaGetLastError());
+  tr("scatter queued");
   c.tm.kernel_launches += 5;  // bbox x3, scatter, sort_cells
   g.built = true;
 }

@@ -20,6 +20,18 @@
 
 #include "ctx.cuh"
 
+// A/B switches of the cooperative match kernel (tools/build_variants.py); the defaults are the
+// measured winners, see profiles/README.md.
+#ifndef SICP_MATCH_C4
+#define SICP_MATCH_C4 0       // 1: request every cell-table entry of step 2 before step 1's records
+#endif
+#ifndef SICP_MATCH_RECPOS
+#define SICP_MATCH_RECPOS 1   // 1: matched point re-read from its (hot) record, 0: from mov_xyz[idx]
+#endif
+#ifndef SICP_MATCH_PREFETCH
+#define SICP_MATCH_PREFETCH 1 // 1: prefetch the query's normal at kernel start
+#endif
+
 namespace sicp {
 
 namespace {
@@ -27,13 +39,17 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // grid engine
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void consider(const Rec& r, double qx, double qy, double qz,
-                                         double& best, long long& bidx) {
+// bpos follows the winner's position in the cell-sorted record array: the record holds the
+// original coordinates, so whoever needs the matched point afterwards re-reads that (cache-hot)
+// record instead of gathering mov_xyz[bidx] from a cold line.
+__device__ __forceinline__ void consider(const Rec& r, uint32_t pos, double qx, double qy, double qz,
+                                         double& best, long long& bidx, uint32_t& bpos) {
   const double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
   const double d2 = dx * dx + dy * dy + dz * dz;
   if (d2 < best || (d2 == best && r.idx < bidx)) {
     best = d2;
     bidx = r.idx;
+    bpos = pos;
   }
 }
 
@@ -42,17 +58,18 @@ __device__ __forceinline__ void consider(const Rec& r, double qx, double qy, dou
 // of branching (a duplicate never changes the result: same distance, same index).
 __device__ __forceinline__ void scan_range(const Rec* __restrict__ recs, uint32_t s, uint32_t e,
                                            double qx, double qy, double qz, double& best,
-                                           long long& bidx) {
+                                           long long& bidx, uint32_t& bpos) {
   for (uint32_t i = s; i < e; i += 4) {
     const uint32_t last = e - 1;
+    const uint32_t i1 = min(i + 1, last), i2 = min(i + 2, last), i3 = min(i + 3, last);
     const Rec r0 = recs[i];
-    const Rec r1 = recs[min(i + 1, last)];
-    const Rec r2 = recs[min(i + 2, last)];
-    const Rec r3 = recs[min(i + 3, last)];
-    consider(r0, qx, qy, qz, best, bidx);
-    consider(r1, qx, qy, qz, best, bidx);
-    consider(r2, qx, qy, qz, best, bidx);
-    consider(r3, qx, qy, qz, best, bidx);
+    const Rec r1 = recs[i1];
+    const Rec r2 = recs[i2];
+    const Rec r3 = recs[i3];
+    consider(r0, i, qx, qy, qz, best, bidx, bpos);
+    consider(r1, i1, qx, qy, qz, best, bidx, bpos);
+    consider(r2, i2, qx, qy, qz, best, bidx, bpos);
+    consider(r3, i3, qx, qy, qz, best, bidx, bpos);
   }
 }
 
@@ -64,6 +81,7 @@ __device__ bool grid_nn(const GridView& g, double qx, double qy, double qz, int 
   const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
   best = kInf;
   bidx = -1;
+  uint32_t bpos = 0;
   const uint32_t* __restrict__ cs = g.cell_start;
   for (int r = 1;; ++r) {
     const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
@@ -75,10 +93,10 @@ __device__ bool grid_nn(const GridView& g, double qx, double qy, double qz, int 
         const long long row = ((long long)z * g.ny + y) * g.nx;
         const bool full = (r == 1) || z == z0 || z == z1 || y == y0 || y == y1;
         if (full) {
-          scan_range(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, best, bidx);
+          scan_range(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, best, bidx, bpos);
         } else {
-          if (x0 >= 0) scan_range(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, best, bidx);
-          if (x1 < g.nx) scan_range(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, best, bidx);
+          if (x0 >= 0) scan_range(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, best, bidx, bpos);
+          if (x1 < g.nx) scan_range(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, best, bidx, bpos);
         }
       }
     }
@@ -104,6 +122,15 @@ __device__ __forceinline__ double plane_distance(const Rigid& T, const double* _
                                                  float4 nrm) {
   double tx, ty, tz;
   rigid_apply(T, mov_xyz[3 * j + 0], mov_xyz[3 * j + 1], mov_xyz[3 * j + 2], tx, ty, tz);
+  const double dx = tx - px, dy = ty - py, dz = tz - pz;
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, (double)nrm.x), __dmul_rn(dy, (double)nrm.y)),
+                   __dmul_rn(dz, (double)nrm.z));
+}
+
+__device__ __forceinline__ double plane_distance_rec(const Rigid& T, const Rec& m, double px, double py,
+                                                     double pz, float4 nrm) {
+  double tx, ty, tz;
+  rigid_apply(T, m.x, m.y, m.z, tx, ty, tz);
   const double dx = tx - px, dy = ty - py, dz = tz - pz;
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, (double)nrm.x), __dmul_rn(dy, (double)nrm.y)),
                    __dmul_rn(dz, (double)nrm.z));
@@ -174,8 +201,13 @@ __global__ void __launch_bounds__(128)
   const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
   const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
   const uint32_t* __restrict__ cs = g.cell_start;
+  // the normal is only needed at the very end: start its (cold) line on the way now
+#if SICP_MATCH_PREFETCH
+  if (with_distance && sub == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(q_nrm + qi));
+#endif
   double best = kInf;
   long long bidx = -1;
+  uint32_t bpos = 0;
   bool resolved = false;
   for (int r = 1;; ++r) {
     const int x0 = cx - r, x1 = cx + r;
@@ -185,20 +217,43 @@ __global__ void __launch_bounds__(128)
       // neighbouring rows, each skipped (or narrowed in x) when the distance from the query to
       // the row / cell already exceeds the best distance of step 1 — the nearest neighbour
       // is usually in the own row, so most of the 27 cells are never read.
-      if (sub < 3) {
+      // The search is a chain of dependent round trips (cell table -> records -> bound -> cell
+      // table -> records), so every cell-table entry step 2 can possibly need — the four
+      // consecutive entries x = cx-1 .. cx+2 of each neighbouring row — is requested here, together
+      // with the own row's, before the first record is touched; step 2 then picks its range
+      // from registers.
+      constexpr int NR = (8 + MG - 1) / MG;  // rows per lane in step 2
+#if SICP_MATCH_C4
+      uint32_t c4[NR][4];
+      bool rv[NR];
+#pragma unroll
+      for (int u = 0; u < NR; ++u) {
+        const int t = sub + u * MG;
+        const int tt = t + (t >= 4 ? 1 : 0);  // 0..8 without the centre (4)
+        const int dz = tt / 3 - 1, dy = tt % 3 - 1;
+        const int y = cy + dy, z = cz + dz;
+        rv[u] = t < 8 && y >= 0 && y < g.ny && z >= 0 && z < g.nz;
+        const long long row = ((long long)z * g.ny + y) * g.nx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c4[u][k] = rv[u] ? cs[row + min(max(cx - 1 + k, 0), g.nx)] : 0u;
+      }
+#endif
+      {
         const int x = cx - 1 + sub;
-        if (x >= 0 && x < g.nx) {
-          const long long row0 = ((long long)cz * g.ny + cy) * g.nx;
-          scan_range(g.recs, cs[row0 + x], cs[row0 + x + 1], qx, qy, qz, best, bidx);
-        }
+        const bool own = sub < 3 && x >= 0 && x < g.nx;
+        const long long row0 = ((long long)cz * g.ny + cy) * g.nx;
+        const uint32_t os = own ? cs[row0 + x] : 0u, oe = own ? cs[row0 + x + 1] : 0u;
+        scan_range(g.recs, os, oe, qx, qy, qz, best, bidx, bpos);
       }
 #pragma unroll
       for (int o = MG / 2; o > 0; o >>= 1) {
         const double od = __shfl_xor_sync(gmask, best, o, MG);
         const long long oi = __shfl_xor_sync(gmask, bidx, o, MG);
+        const uint32_t op = __shfl_xor_sync(gmask, bpos, o, MG);
         if (od < best || (od == best && oi >= 0 && (bidx < 0 || oi < bidx))) {
           best = od;
           bidx = oi;
+          bpos = op;
         }
       }
       // distances from the query to the faces of its own cell (>= 0 up to rounding)
@@ -206,7 +261,25 @@ __global__ void __launch_bounds__(128)
       const double fyl = fmax(qy - (g.oy + cy * g.h), 0.0), fyh = fmax((g.oy + (cy + 1) * g.h) - qy, 0.0);
       const double fzl = fmax(qz - (g.oz + cz * g.h), 0.0), fzh = fmax((g.oz + (cz + 1) * g.h) - qz, 0.0);
       const double lim = best * (1.0 + 1e-12);  // strictly farther only: ties are still visited
-      constexpr int NR = (8 + MG - 1) / MG;  // rows per lane in step 2
+#if SICP_MATCH_C4
+#pragma unroll
+      for (int u = 0; u < NR; ++u) {
+        const int t = sub + u * MG;
+        const int tt = t + (t >= 4 ? 1 : 0);
+        const int dz = tt / 3 - 1, dy = tt % 3 - 1;
+        const double by = (dy < 0) ? fyl : ((dy > 0) ? fyh : 0.0);
+        const double bz = (dz < 0) ? fzl : ((dz > 0) ? fzh : 0.0);
+        const double lb = by * by + bz * bz;
+        uint32_t rs = 0, re = 0;
+        if (rv[u] && !(lb > lim)) {
+          // c4[k] = cell_start[row + cx - 1 + k] (clamped): [0] = start of x = cx-1, [1] = start of cx,
+          // [2] = end of cx, [3] = end of cx+1
+          rs = (x0 >= 0 && lb + fxl * fxl > lim) ? c4[u][1] : c4[u][0];
+          re = (x1 < g.nx && lb + fxh * fxh > lim) ? c4[u][2] : c4[u][3];
+        }
+        scan_range(g.recs, rs, re, qx, qy, qz, best, bidx, bpos);
+      }
+#else
       uint32_t rs[NR], re[NR];
 #pragma unroll
       for (int u = 0; u < NR; ++u) {
@@ -229,7 +302,8 @@ __global__ void __launch_bounds__(128)
         re[u] = cs[row + xe + 1];
       }
 #pragma unroll
-      for (int u = 0; u < NR; ++u) scan_range(g.recs, rs[u], re[u], qx, qy, qz, best, bidx);
+      for (int u = 0; u < NR; ++u) scan_range(g.recs, rs[u], re[u], qx, qy, qz, best, bidx, bpos);
+#endif
     } else {
       const int side = 2 * r + 1, items = side * side;
       for (int t = sub; t < items; t += MG) {
@@ -239,10 +313,10 @@ __global__ void __launch_bounds__(128)
         const long long row = ((long long)z * g.ny + y) * g.nx;
         const bool full = dy == -r || dy == r || dz == -r || dz == r;
         if (full) {
-          scan_range(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, best, bidx);
+          scan_range(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, best, bidx, bpos);
         } else {
-          if (x0 >= 0) scan_range(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, best, bidx);
-          if (x1 < g.nx) scan_range(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, best, bidx);
+          if (x0 >= 0) scan_range(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, best, bidx, bpos);
+          if (x1 < g.nx) scan_range(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, best, bidx, bpos);
         }
       }
     }
@@ -251,9 +325,11 @@ __global__ void __launch_bounds__(128)
     for (int o = MG / 2; o > 0; o >>= 1) {
       const double od = __shfl_xor_sync(gmask, best, o, MG);
       const long long oi = __shfl_xor_sync(gmask, bidx, o, MG);
+      const uint32_t op = __shfl_xor_sync(gmask, bpos, o, MG);
       if (od < best || (od == best && oi >= 0 && (bidx < 0 || oi < bidx))) {
         best = od;
         bidx = oi;
+        bpos = op;
       }
     }
     const int y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
@@ -284,7 +360,13 @@ __global__ void __launch_bounds__(128)
   nn_idx[qi] = bidx;
   if (with_distance) {
     const float4 nr = q_nrm[qi];
+    // the winner's record was read a moment ago by a lane of this warp: same coordinates as
+    // mov_xyz[bidx], but from L1/L2 instead of a cold line
+#if SICP_MATCH_RECPOS
+    const double d = plane_distance_rec(st->T, g.recs[bpos], px, py, pz, nr);
+#else
     const double d = plane_distance(st->T, mov_xyz, bidx, px, py, pz, nr);
+#endif
     out[qi] = d;
     lin_hist_add(st, lin_hist, nr.w, d);
   } else {

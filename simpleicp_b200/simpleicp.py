@@ -74,8 +74,19 @@ def _change(new: float, old: float) -> float:
 class _Result:
     """Everything one registration produces."""
 
-    __slots__ = ("H", "X_mov_transformed", "rbp", "residuals", "idx_selected", "normals",
+    __slots__ = ("H", "X_mov_transformed", "rbp", "residuals", "_idx", "normals",
                  "records", "iterations", "converged", "timings", "loop_ms", "initial_stats")
+
+    @property
+    def idx_selected(self):
+        """Indices of the selected fixed points (computed on first use after a fused run)."""
+        if callable(self._idx):
+            self._idx = self._idx()
+        return self._idx
+
+    @idx_selected.setter
+    def idx_selected(self, v):
+        self._idx = v
 
 
 def _wrap_error(e: _capi.SicpError, max_overlap_distance: float):
@@ -129,7 +140,15 @@ def register(
     )
     own = engine is None
     eng = engine or _capi.Engine()
+    fused = (idx_selected is None and normals is None and not stepwise and on_normals is None
+             and not want_normals)
     try:
+        if fused:
+            # the whole of SimpleICP.run as one library call: nothing but the clouds goes in,
+            # nothing but the results comes back (simpleicp_b200/_capi.py::register_fused)
+            return _register_fused(eng, X_fix, X_mov, correspondences, neighbors, min_planarity,
+                                   max_overlap_distance, min_change, max_iterations, distance_weights,
+                                   obs, w_obs, rbp_observation_weights, transform_out)
         eng.set_clouds(X_fix, X_mov)
         n_fix = eng.n_fix
         idx = None if idx_selected is None else np.asarray(idx_selected, dtype=np.int64)
@@ -178,14 +197,7 @@ def register(
             raise _wrap_error(e, max_overlap_distance) from None
         x, sigma, H, residuals, records, iterations, converged, loop_ms = out
 
-        rbp = optimization.RigidBodyParameters()
-        rbp.set_parameter_attributes_from_list(
-            "initial_value", list(obs) if iterations <= 1 else list(records[iterations - 2]["x"])
-        )
-        rbp.set_parameter_attributes_from_list("observed_value", list(obs))
-        rbp.set_parameter_attributes_from_list("observation_weight", list(rbp_observation_weights))
-        rbp.set_parameter_attributes_from_list("estimated_value", [float(v) for v in x])
-        rbp.set_parameter_attributes_from_list("estimated_uncertainty", [float(v) for v in sigma])
+        rbp = _make_rbp(obs, rbp_observation_weights, records, iterations, x, sigma)
 
         _log_run(records, iterations, converged, H, rbp)
 
@@ -205,18 +217,67 @@ def register(
             eng.close()
 
 
-def _loop_fused(eng: _capi.Engine, params):
-    out, log, residuals = eng.run(params)
-    records = [
+def _records(log):
+    return [
         dict(n_kept=int(r.n_kept), median=r.median, mad=r.mad, mean_dist=r.mean_dist,
              std_dist=r.std_dist, x=np.array(r.x), mean_res=r.mean_res, std_res=r.std_res,
              distance_weight=r.distance_weight, lm_iterations=int(r.lm_iterations),
              n_bruteforce=int(r.n_bruteforce))
         for r in log
     ]
+
+
+def _loop_fused(eng: _capi.Engine, params):
+    out, log, residuals = eng.run(params)
     H = np.array(out.H).reshape(4, 4)
-    return (np.array(out.x), np.array(out.sigma), H, residuals, records, int(out.iterations),
+    return (np.array(out.x), np.array(out.sigma), H, residuals, _records(log), int(out.iterations),
             bool(out.converged), float(out.loop_ms))
+
+
+def _make_rbp(obs, rbp_observation_weights, records, iterations, x, sigma):
+    rbp = optimization.RigidBodyParameters()
+    rbp.set_parameter_attributes_from_list(
+        "initial_value", list(obs) if iterations <= 1 else list(records[iterations - 2]["x"])
+    )
+    rbp.set_parameter_attributes_from_list("observed_value", list(obs))
+    rbp.set_parameter_attributes_from_list("observation_weight", list(rbp_observation_weights))
+    rbp.set_parameter_attributes_from_list("estimated_value", [float(v) for v in x])
+    rbp.set_parameter_attributes_from_list("estimated_uncertainty", [float(v) for v in sigma])
+    return rbp
+
+
+def _register_fused(eng, X_fix, X_mov, correspondences, neighbors, min_planarity, max_overlap_distance,
+                    min_change, max_iterations, distance_weights, obs, w_obs, rbp_observation_weights,
+                    transform_out) -> _Result:
+    for msg in ("Consider partial overlap of point clouds ..." if np.isfinite(max_overlap_distance) else None,
+                "Select points for correspondences in fixed point cloud ...",
+                "Estimate normals of selected points ...", "Start iterations ..."):
+        if msg:
+            _log.info(msg)
+    lsq = eng.lsq_params(obs, obs, w_obs, distance_weights)
+    params = eng.run_params(min_planarity, min_change, max_iterations, lsq)
+    try:
+        out, log, residuals, X_t = eng.register_fused(
+            X_fix, X_mov, correspondences, neighbors,
+            max_overlap_distance if np.isfinite(max_overlap_distance) else -1.0, params, transform_out)
+    except _capi.SicpError as e:
+        raise _wrap_error(e, max_overlap_distance) from None
+    records, iterations = _records(log), int(out.iterations)
+    H = np.array(out.H).reshape(4, 4)
+    rbp = _make_rbp(obs, rbp_observation_weights, records, iterations, np.array(out.x), np.array(out.sigma))
+    _log_run(records, iterations, bool(out.converged), H, rbp)
+    r = _Result()
+    r.H, r.X_mov_transformed, r.rbp, r.residuals = H, X_t, rbp, residuals
+    if np.isfinite(max_overlap_distance):
+        r.idx_selected = eng.select_n_points(eng.K)  # no-op on the selection, downloads it
+    else:
+        n_fix, K = eng.n_fix, eng.K
+        r.idx_selected = lambda: (pointcloud.subsample_indices(n_fix, K).astype(np.int64) if K < n_fix
+                                  else np.arange(n_fix, dtype=np.int64))
+    r.normals, r.records = None, records
+    r.iterations, r.converged, r.loop_ms = iterations, bool(out.converged), float(out.loop_ms)
+    r.timings = eng.timings()
+    return r
 
 
 def _loop_stepwise(eng, params, obs, w_obs, distance_weights, min_planarity, min_change,

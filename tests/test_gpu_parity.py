@@ -621,3 +621,52 @@ def test_single_iteration_and_fixed_parameters(gpu):
     o = O.simpleicp(X_fix, X_mov, rbp_observed_values=obs, rbp_observation_weights=w, max_iterations=3,
                     normals=(np.column_stack(res.normals[:3]), res.normals[3]))
     assert abs(x[5] - o[2][5]) < 1e-6
+
+
+@pytest.mark.parametrize("name,kw", [("dragon", {}), ("bunny", {"max_overlap_distance": 1.0}),
+                                     ("multisensor", {"correspondences": 5000})])
+def test_fused_register_equals_stage_by_stage(gpu, name, kw):
+    """sicp_register (one call, movable upload overlapped with the fixed-side work) against the
+    stage-by-stage sequence it is defined to equal: bit-identical results."""
+    X_fix, X_mov = load_pair(name)
+    eng = _capi.Engine()
+    try:
+        a = sb.register(X_fix, X_mov, engine=eng, want_normals=True, **kw)    # staged
+        b = sb.register(X_fix, X_mov, engine=eng, want_normals=False, **kw)   # fused
+        assert b.normals is None and a.normals is not None
+        assert np.array_equal(a.H, b.H) and a.iterations == b.iterations and a.converged == b.converged
+        assert np.array_equal(a.residuals, b.residuals)
+        assert np.array_equal(np.asarray(a.X_mov_transformed), np.asarray(b.X_mov_transformed))
+        assert np.array_equal(a.idx_selected, b.idx_selected)
+        for ra, rb in zip(a.records, b.records):
+            assert ra["n_kept"] == rb["n_kept"] and ra["mean_res"] == rb["mean_res"] and ra["std_res"] == rb["std_res"]
+        # the stage-by-stage API stays usable on the state the fused call left behind
+        assert eng.K == a.idx_selected.size
+        nn_idx, d = eng.match(a.H)
+        assert nn_idx.shape == (eng.K,)
+    finally:
+        eng.close()
+    with pytest.raises(sb.SimpleICPException, match="do not overlap"):
+        sb.simpleicp(X_fix, X_mov + 1e5, max_overlap_distance=1.0)
+
+
+def test_select_n_points_on_device(gpu):
+    """sicp_select_n_points = PointCloud.select_n_points (pointcloud.py:121-147): numpy linspace
+    arithmetic and round-half-even; the linearised variants round half away from zero."""
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(5000, 3))
+    with _capi.Engine() as e:
+        e.set_clouds(X, X + 0.01)
+        for m_idx, n in ((None, 1000), (None, 1), (None, 4999), (None, 5000), (None, 7000), (np.arange(3, 4000, 3), 77)):
+            e.set_selected(m_idx)
+            base = np.arange(5000) if m_idx is None else m_idx
+            got = e.select_n_points(n)
+            want = base if n >= base.size else base[sb.pointcloud.subsample_indices(base.size, n)]
+            assert np.array_equal(got, want), (n, got[:5], want[:5])
+            assert e.K == want.size
+        # 10 points -> 5: linspace = 0 2.25 4.5 6.75 9; rint -> 0 2 4 7 9, C round() -> 0 2 5 7 9
+        e.set_selected(np.arange(10))
+        assert e.select_n_points(5).tolist() == [0, 2, 4, 7, 9]
+        e.set_option("variant", 1)
+        e.set_selected(np.arange(10))
+        assert e.select_n_points(5).tolist() == [0, 2, 5, 7, 9]
