@@ -20,18 +20,6 @@
 
 #include "ctx.cuh"
 
-// A/B switches of the cooperative match kernel (tools/build_variants.py); the defaults are the
-// measured winners, see profiles/README.md.
-#ifndef SICP_MATCH_C4
-#define SICP_MATCH_C4 0       // 1: request every cell-table entry of step 2 before step 1's records
-#endif
-#ifndef SICP_MATCH_RECPOS
-#define SICP_MATCH_RECPOS 1   // 1: matched point re-read from its (hot) record, 0: from mov_xyz[idx]
-#endif
-#ifndef SICP_MATCH_PREFETCH
-#define SICP_MATCH_PREFETCH 1 // 1: prefetch the query's normal at kernel start
-#endif
-
 namespace sicp {
 
 namespace {
@@ -202,9 +190,7 @@ __global__ void __launch_bounds__(128)
   const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
   const uint32_t* __restrict__ cs = g.cell_start;
   // the normal is only needed at the very end: start its (cold) line on the way now
-#if SICP_MATCH_PREFETCH
   if (with_distance && sub == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(q_nrm + qi));
-#endif
   double best = kInf;
   long long bidx = -1;
   uint32_t bpos = 0;
@@ -217,27 +203,11 @@ __global__ void __launch_bounds__(128)
       // neighbouring rows, each skipped (or narrowed in x) when the distance from the query to
       // the row / cell already exceeds the best distance of step 1 — the nearest neighbour
       // is usually in the own row, so most of the 27 cells are never read.
-      // The search is a chain of dependent round trips (cell table -> records -> bound -> cell
-      // table -> records), so every cell-table entry step 2 can possibly need — the four
-      // consecutive entries x = cx-1 .. cx+2 of each neighbouring row — is requested here, together
-      // with the own row's, before the first record is touched; step 2 then picks its range
-      // from registers.
+      // (Requesting every cell-table entry step 2 might need before step 1's records — to shorten
+      // the chain of dependent round trips — was measured 10 % SLOWER: the kernel is bound by
+      // issue slots as much as by latency, and 8 extra loads per lane cost more than the round
+      // trip they save; profiles/README.md.)
       constexpr int NR = (8 + MG - 1) / MG;  // rows per lane in step 2
-#if SICP_MATCH_C4
-      uint32_t c4[NR][4];
-      bool rv[NR];
-#pragma unroll
-      for (int u = 0; u < NR; ++u) {
-        const int t = sub + u * MG;
-        const int tt = t + (t >= 4 ? 1 : 0);  // 0..8 without the centre (4)
-        const int dz = tt / 3 - 1, dy = tt % 3 - 1;
-        const int y = cy + dy, z = cz + dz;
-        rv[u] = t < 8 && y >= 0 && y < g.ny && z >= 0 && z < g.nz;
-        const long long row = ((long long)z * g.ny + y) * g.nx;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c4[u][k] = rv[u] ? cs[row + min(max(cx - 1 + k, 0), g.nx)] : 0u;
-      }
-#endif
       {
         const int x = cx - 1 + sub;
         const bool own = sub < 3 && x >= 0 && x < g.nx;
@@ -261,25 +231,6 @@ __global__ void __launch_bounds__(128)
       const double fyl = fmax(qy - (g.oy + cy * g.h), 0.0), fyh = fmax((g.oy + (cy + 1) * g.h) - qy, 0.0);
       const double fzl = fmax(qz - (g.oz + cz * g.h), 0.0), fzh = fmax((g.oz + (cz + 1) * g.h) - qz, 0.0);
       const double lim = best * (1.0 + 1e-12);  // strictly farther only: ties are still visited
-#if SICP_MATCH_C4
-#pragma unroll
-      for (int u = 0; u < NR; ++u) {
-        const int t = sub + u * MG;
-        const int tt = t + (t >= 4 ? 1 : 0);
-        const int dz = tt / 3 - 1, dy = tt % 3 - 1;
-        const double by = (dy < 0) ? fyl : ((dy > 0) ? fyh : 0.0);
-        const double bz = (dz < 0) ? fzl : ((dz > 0) ? fzh : 0.0);
-        const double lb = by * by + bz * bz;
-        uint32_t rs = 0, re = 0;
-        if (rv[u] && !(lb > lim)) {
-          // c4[k] = cell_start[row + cx - 1 + k] (clamped): [0] = start of x = cx-1, [1] = start of cx,
-          // [2] = end of cx, [3] = end of cx+1
-          rs = (x0 >= 0 && lb + fxl * fxl > lim) ? c4[u][1] : c4[u][0];
-          re = (x1 < g.nx && lb + fxh * fxh > lim) ? c4[u][2] : c4[u][3];
-        }
-        scan_range(g.recs, rs, re, qx, qy, qz, best, bidx, bpos);
-      }
-#else
       uint32_t rs[NR], re[NR];
 #pragma unroll
       for (int u = 0; u < NR; ++u) {
@@ -303,7 +254,6 @@ __global__ void __launch_bounds__(128)
       }
 #pragma unroll
       for (int u = 0; u < NR; ++u) scan_range(g.recs, rs[u], re[u], qx, qy, qz, best, bidx, bpos);
-#endif
     } else {
       const int side = 2 * r + 1, items = side * side;
       for (int t = sub; t < items; t += MG) {
@@ -362,11 +312,7 @@ __global__ void __launch_bounds__(128)
     const float4 nr = q_nrm[qi];
     // the winner's record was read a moment ago by a lane of this warp: same coordinates as
     // mov_xyz[bidx], but from L1/L2 instead of a cold line
-#if SICP_MATCH_RECPOS
     const double d = plane_distance_rec(st->T, g.recs[bpos], px, py, pz, nr);
-#else
-    const double d = plane_distance(st->T, mov_xyz, bidx, px, py, pz, nr);
-#endif
     out[qi] = d;
     lin_hist_add(st, lin_hist, nr.w, d);
   } else {

@@ -106,14 +106,23 @@ def simpleicp_linearized(
     try:
         say("Create point cloud objects ...")
         eng.set_option("variant", VARIANT_LINEARIZED_CPP if compose == "H*dH" else VARIANT_LINEARIZED)
-        eng.set_clouds(X_fix, X_mov)
-        n_fix = eng.n_fix
-        idx = None
-        if max_overlap_distance > 0 and np.isfinite(max_overlap_distance):
-            say("Consider partial overlap of point clouds ...")
-            eng.set_selected(None)
+        zero = [0.0] * 6
+        params = eng.run_params(min_planarity, min_change, max_iterations,
+                                eng.lsq_params(zero, zero, zero, 1.0))
+        has_filter = max_overlap_distance > 0 and np.isfinite(max_overlap_distance)
+        X_t = None
+        if normals is None and not want_normals:
+            # the whole driver as one library call (sicp_register; the variant option selects the
+            # native rounding of the subsample and the linearised loop)
+            for msg in ("Consider partial overlap of point clouds ..." if has_filter else None,
+                        "Select points for correspondences in fixed point cloud ...",
+                        "Estimate normals of selected points ...", "Start iterations ..."):
+                if msg:
+                    say(msg)
             try:
-                keep = eng.select_in_range(np.eye(4), float(max_overlap_distance))
+                out, log, _, X_t = eng.register_fused(X_fix, X_mov, correspondences, neighbors,
+                                                      max_overlap_distance if has_filter else -1.0, params,
+                                                      transform_out)
             except _capi.SicpError as e:
                 if e.code == _capi.SICP_ERR_NO_OVERLAP:
                     raise RuntimeError(
@@ -121,26 +130,41 @@ def simpleicp_linearized(
                         "Consider increasing the value of max_overlap_distance." % max_overlap_distance
                     ) from None
                 raise
-            idx = np.arange(n_fix, dtype=np.int64)[keep]
-        say("Select points for correspondences in fixed point cloud ...")
-        m = n_fix if idx is None else idx.size
-        if correspondences < m:
-            pick = subsample_indices_cpp(m, correspondences)
-            idx = (pick if idx is None else idx[pick]).astype(np.int64)
-        eng.set_selected(idx)
-        if idx is None:
-            idx = np.arange(n_fix, dtype=np.int64)
-        if normals is None:
-            say("Estimate normals of selected points ...")
-            nrm = eng.estimate_normals(neighbors, download=want_normals)
+            nrm = None
+            idx = eng.select_n_points(eng.K)  # downloads the selection (no-op on the device)
         else:
-            nrm = tuple(np.asarray(a, dtype=np.float32) for a in normals)
-            eng.set_normals(*nrm)
-        say("Start iterations ...")
-        zero = [0.0] * 6
-        params = eng.run_params(min_planarity, min_change, max_iterations,
-                                eng.lsq_params(zero, zero, zero, 1.0))
-        out, log, _ = eng.run(params)
+            eng.set_clouds(X_fix, X_mov)
+            n_fix = eng.n_fix
+            idx = None
+            if has_filter:
+                say("Consider partial overlap of point clouds ...")
+                eng.set_selected(None)
+                try:
+                    keep = eng.select_in_range(np.eye(4), float(max_overlap_distance))
+                except _capi.SicpError as e:
+                    if e.code == _capi.SICP_ERR_NO_OVERLAP:
+                        raise RuntimeError(
+                            "Point clouds do not overlap within max_overlap_distance = %.5f. "
+                            "Consider increasing the value of max_overlap_distance." % max_overlap_distance
+                        ) from None
+                    raise
+                idx = np.arange(n_fix, dtype=np.int64)[keep]
+            say("Select points for correspondences in fixed point cloud ...")
+            m = n_fix if idx is None else idx.size
+            if correspondences < m:
+                pick = subsample_indices_cpp(m, correspondences)
+                idx = (pick if idx is None else idx[pick]).astype(np.int64)
+            eng.set_selected(idx)
+            if idx is None:
+                idx = np.arange(n_fix, dtype=np.int64)
+            if normals is None:
+                say("Estimate normals of selected points ...")
+                nrm = eng.estimate_normals(neighbors, download=want_normals)
+            else:
+                nrm = tuple(np.asarray(a, dtype=np.float32) for a in normals)
+                eng.set_normals(*nrm)
+            say("Start iterations ...")
+            out, log, _ = eng.run(params)
         records = [
             dict(n_kept=int(r.n_kept), median=r.median, mad=r.mad, mean_dist=r.mean_dist,
                  std_dist=r.std_dist, x=np.array(r.x), mean_res=r.mean_res, std_res=r.std_res,
@@ -157,7 +181,7 @@ def simpleicp_linearized(
         say(res.table)
         say("Estimated transformation matrix H:")
         say(format_matrix(res.H))
-        res.X_mov_transformed = eng.transform(res.T, out=transform_out)
+        res.X_mov_transformed = X_t if X_t is not None else eng.transform(res.T, out=transform_out)
         say("Finished in %.3f seconds!" % (time.time() - t0))
         return res
     finally:

@@ -47,6 +47,8 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu\n", offsetof(sicp_run_params, lsq), offsetof(sicp_iter_record, x),
          offsetof(sicp_iter_record, lm_iterations), offsetof(sicp_run_result, H),
          offsetof(sicp_run_result, loop_ms));
+  printf("%zu %zu %zu\n", sizeof(sicp_register_params), offsetof(sicp_register_params, max_overlap_distance),
+         offsetof(sicp_register_params, run));
   return 0;
 }
 """)
@@ -57,7 +59,9 @@ int main(void) {
     want = [C.sizeof(_capi.LsqParams), C.sizeof(_capi.RunParams), C.sizeof(_capi.IterRecord),
             C.sizeof(_capi.RunResult), C.sizeof(_capi.Timings), _capi.RunParams.lsq.offset,
             _capi.IterRecord.x.offset, _capi.IterRecord.lm_iterations.offset,
-            _capi.RunResult.H.offset, _capi.RunResult.loop_ms.offset]
+            _capi.RunResult.H.offset, _capi.RunResult.loop_ms.offset,
+            C.sizeof(_capi.RegisterParams), _capi.RegisterParams.max_overlap_distance.offset,
+            _capi.RegisterParams.run.offset]
     assert got == want
 
 

@@ -88,7 +88,11 @@ def test_own_normals_chain(gpu, name):
     the result moves only at the level the data's noise allows (1e-5 on the noise-free pair)."""
     X_fix, X_mov = CASES[name]["pair"]()
     kw = CASES[name]["kw"]
-    res = sb.simpleicp_linearized(X_fix, X_mov, want_normals=True, **kw)
+    res = sb.simpleicp_linearized(X_fix, X_mov, want_normals=True, **kw)      # stage by stage
+    fused = sb.simpleicp_linearized(X_fix, X_mov, **kw)                       # one sicp_register call
+    assert np.array_equal(res.T, fused.T) and res.iterations == fused.iterations
+    assert np.array_equal(res.idx_selected, fused.idx_selected)
+    assert np.array_equal(np.asarray(res.X_mov_transformed), np.asarray(fused.X_mov_transformed))
     ref64 = LO.simpleicp_linearized(X_fix, X_mov, compose="pre", **kw)
     n_gpu = np.stack([np.asarray(a, dtype=np.float64) for a in res.normals[:3]], axis=1)
     p_gpu = np.asarray(res.normals[3], dtype=np.float64)
