@@ -256,8 +256,15 @@ __global__ void __launch_bounds__(128)
       for (int u = 0; u < NR; ++u) scan_range(g.recs, rs[u], re[u], qx, qy, qz, best, bidx, bpos);
     } else {
       const int side = 2 * r + 1, items = side * side;
-      for (int t = sub; t < items; t += MG) {
-        const int dz = t / side - r, dy = t % side - r;
+      // (dy, dz) walk the (2r+1)^2 rows with stride MG; kept incrementally — two integer
+      // divisions by the run-time `side` per row were a third of the instructions of this loop
+      int dzr = sub / side, dyr = sub - dzr * side;
+      for (int t = sub; t < items; t += MG, dyr += MG) {
+        while (dyr >= side) {
+          dyr -= side;
+          ++dzr;
+        }
+        const int dz = dzr - r, dy = dyr - r;
         const int y = cy + dy, z = cz + dz;
         if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
         const long long row = ((long long)z * g.ny + y) * g.nx;
