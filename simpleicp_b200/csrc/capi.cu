@@ -580,6 +580,8 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
   };
   init_state(c, p->lsq.x0, nullptr, true);
   std::memset(out, 0, sizeof(*out));
+  // iterations queued past the stop flag return without writing their record: keep the slots defined
+  SICP_CUDA(cudaMemsetAsync(c.ws.rec.p, 0, sizeof(sicp_iter_record) * (size_t)p->max_iterations, c.stream));
   tr("init", -1);
 
   cudaEvent_t e0, e1;
