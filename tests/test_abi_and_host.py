@@ -77,6 +77,24 @@ def test_no_cpu_fallback_without_device():
         sb.simpleicp(X_fix, X_mov)
 
 
+def test_cli_and_linearized_fail_loudly_without_device(tmp_path):
+    """No CPU path anywhere: the command line and the linearised front end error out too."""
+    from conftest import has_gpu
+
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    X_fix, X_mov = load_pair("bunny")
+    with pytest.raises(_capi.SicpError):
+        sb.simpleicp_linearized(X_fix, X_mov)
+    f = tmp_path / "a.xyz"
+    sb.write_xyz(f, X_fix[:100], decimals=4, header=False)
+    cli = REPO / "simpleicp_b200" / "sicp_cli"
+    r = subprocess.run([str(cli), "-f", str(f), "-m", str(f)], capture_output=True, text=True)
+    assert r.returncode == 1 and "Caught exception: no CUDA device available" in r.stderr
+    h = subprocess.run([str(cli), "--help"], capture_output=True, text=True)
+    assert h.returncode == 0 and "--variant" in h.stdout and "--max_overlap_distance" in h.stdout
+
+
 def test_product_does_not_import_oracle():
     for f in (REPO / "simpleicp_b200").glob("*.py"):
         assert "oracle" not in f.read_text().replace("oracle/make_golden", ""), f
