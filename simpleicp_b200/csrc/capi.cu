@@ -358,7 +358,8 @@ int32_t sicp_select_in_range(sicp_ctx* ctx, const double H0[16], double max_rang
   c.dist.reserve(c.K);
   c.keep.reserve(c.K);
   // the overlap filter needs no normals: the epilogue is skipped (with_distance = false)
-  match_launch(c, false, c.dist.p);
+  // only the side of max_range matters: bounded search (nn.cu: grid_nn, cap2)
+  match_launch(c, false, c.dist.p, nullptr, true, max_range * max_range);
   SICP_CUDA(cudaMemsetAsync(c.misc_counters.p + 8, 0, sizeof(unsigned int), c.stream));
   k_range_keep<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(
       c.dist.p, c.K, max_range * max_range, c.keep.p, c.misc_counters.p + 8);
@@ -800,7 +801,7 @@ int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, const
     StageTimer t(c, &c.tm.overlap_ms);
     c.dist.reserve(c.K);
     c.keep.reserve(c.K);
-    match_launch(c, false, c.dist.p);
+    match_launch(c, false, c.dist.p, nullptr, true, rp->max_overlap_distance * rp->max_overlap_distance);
     SICP_CUDA(cudaMemsetAsync(c.misc_counters.p + 8, 0, sizeof(unsigned int), c.stream));
     k_range_keep<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(
         c.dist.p, c.K, rp->max_overlap_distance * rp->max_overlap_distance, c.keep.p, c.misc_counters.p + 8);

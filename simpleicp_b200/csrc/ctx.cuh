@@ -136,7 +136,7 @@ void make_float4_copy(Ctx& c);
 // allow_bf: bound the ring expansion by grid_max_rings and answer the rest with the brute-force
 // pass; otherwise the grid search runs to completion on its own (no extra launches).
 void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid = nullptr,
-                  bool allow_bf = true);
+                  bool allow_bf = true, double cap2 = -1.0);
 void set_state_transform(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_loop);
 void estimate_normals_launch(Ctx& c, int k);
 void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve, bool arm_stop,

@@ -62,8 +62,11 @@ __device__ __forceinline__ void scan_range(const Rec* __restrict__ recs, uint32_
 }
 
 // Returns true when (best, bidx) is proven to be the nearest neighbour.
-__device__ bool grid_nn(const GridView& g, double qx, double qy, double qz, int rmax, double& best,
-                        long long& bidx) {
+// cap2 >= 0: the caller only needs to know on which side of cap2 the squared nearest-neighbour
+// distance lies (overlap filter, PointCloud.select_in_range): the search may stop as soon as any
+// point closer than the bound is found, or once every unexplored cell is farther than the bound.
+__device__ bool grid_nn(const GridView& g, double qx, double qy, double qz, int rmax, double cap2,
+                        double& best, long long& bidx) {
   const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
   const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
   const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
@@ -99,6 +102,7 @@ __device__ bool grid_nn(const GridView& g, double qx, double qy, double qz, int 
     if (guard >= kInf) return true;  // the block covers the whole grid
     guard -= 1e-9 * g.h;             // cell assignment of points rounds at the 1e-13 level
     if (guard > 0.0 && best <= guard * guard) return true;
+    if (cap2 >= 0.0 && (best < cap2 || (guard > 0.0 && guard * guard >= cap2))) return true;
     if (r >= rmax) return false;
   }
 }
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(128)
                  const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz, long long K,
                  int rmax, int with_distance, long long* __restrict__ nn_idx,
                  double* __restrict__ out, unsigned int* __restrict__ unresolved,
-                 unsigned int* __restrict__ lin_hist) {
+                 unsigned int* __restrict__ lin_hist, double cap2) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= K || st->stop) return;
   const Rigid Tinv = st->Tinv;
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(128)
   rigid_apply(Tinv, px, py, pz, qx, qy, qz);
   double best;
   long long bidx;
-  const bool ok = grid_nn(g, qx, qy, qz, rmax, best, bidx);
+  const bool ok = grid_nn(g, qx, qy, qz, rmax, cap2, best, bidx);
   if (!ok) {
     const unsigned int slot = atomicAdd(&unresolved[K], 1u);
     unresolved[slot] = (unsigned int)i;
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(128)
                       const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz,
                       long long K, int rmax, int with_distance, long long* __restrict__ nn_idx,
                       double* __restrict__ out, unsigned int* __restrict__ unresolved,
-                      unsigned int* __restrict__ lin_hist) {
+                      unsigned int* __restrict__ lin_hist, double cap2) {
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long qi = gt / MG;
   const int sub = threadIdx.x & (MG - 1);
@@ -304,6 +308,10 @@ __global__ void __launch_bounds__(128)
     guard -= 1e-9 * g.h;
     if (guard > 0.0 && best <= guard * guard) {
       resolved = true;
+      break;
+    }
+    if (cap2 >= 0.0 && (best < cap2 || (guard > 0.0 && guard * guard >= cap2))) {
+      resolved = true;  // overlap filter: the side of the bound is decided (see grid_nn)
       break;
     }
     if (r >= rmax) break;
@@ -658,7 +666,7 @@ static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
   c.tm.kernel_launches += 2;
 }
 
-void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, bool allow_bf) {
+void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, bool allow_bf, double cap2) {
   const long long K = c.K;
   // predictor histogram for the reject kernel: zero it if an earlier match filled it and no
   // reject consumed it (the reject kernel itself leaves it zeroed)
@@ -684,7 +692,7 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   if (c.match_group == 1) {
     k_match_grid<<<(unsigned)((K + 127) / 128), 128, 0, c.stream>>>(
         c.gmov.view(), c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p, K, rmax,
-        with_distance ? 1 : 0, c.nn_idx.p, out, c.unresolved.p, lh);
+        with_distance ? 1 : 0, c.nn_idx.p, out, c.unresolved.p, lh, cap2);
   } else {
     // lanes per query: 16 while the search is latency-bound (few queries), fewer once there are
     // enough queries to fill the machine and issue slots become the limit
@@ -696,7 +704,7 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   k_match_grid_coop<N><<<blocks, 128, 0, c.stream>>>(c.gmov.view(), c.dev_state.p, c.q_xyz.p, \
                                                     c.q_nrm.p, c.mov_xyz.p, K, rmax,          \
                                                     with_distance ? 1 : 0, c.nn_idx.p, out,   \
-                                                    c.unresolved.p, lh)
+                                                    c.unresolved.p, lh, cap2)
     if (mg == 4) SICP_LAUNCH_COOP(4);
     else if (mg == 8) SICP_LAUNCH_COOP(8);
     else SICP_LAUNCH_COOP(16);
