@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SICP_ABI_VERSION 1
+#define SICP_ABI_VERSION 2
 
 typedef enum {
   SICP_OK = 0,

@@ -67,6 +67,8 @@ CONFIGS = {
     ),
 }
 TRAVEL = ("dragon", "bunny", "multisensor", "webots")  # inputs committed as fixtures
+TRAVEL_LARGE = ("airborne", "terrestrial")  # > 1M points each: delta + byte-plane + LZMA (see below)
+DEBUG_DUMPS = ("bunny",)  # configs whose debug_dirpath output is captured (debug_<name>.npz)
 
 
 def save_cloud_fixture(name, X_fix, X_mov):
@@ -84,11 +86,105 @@ def save_cloud_fixture(name, X_fix, X_mov):
     np.savez_compressed(GOLD / f"data_{name}.npz", fix=fi, mov=mi, scale=np.int64(s))
 
 
+def encode_cloud(X):
+    """Lossless compact form of a fixed-decimal scan-ordered cloud: scaled int32, first
+    differences along the scan, zig-zag, the four byte planes of every column stored one after
+    the other (the high planes are almost all zero), LZMA.  5.7 MB for the 1.34 M-point airborne
+    cloud (32 MB of text).  tests/conftest.py::decode_cloud is the inverse."""
+    import lzma
+
+    for dec in range(0, 7):
+        s = 10 ** dec
+        if np.array_equal(np.round(X * s) / s, X):
+            break
+    else:
+        raise RuntimeError("cloud is not a fixed-decimal text file")
+    I = np.round(X * s).astype(np.int64)
+    assert np.abs(I).max() < 2 ** 30 and np.array_equal(I / s, X)
+    D = np.diff(I, axis=0, prepend=0).astype(np.int32)
+    Z = ((D << 1) ^ (D >> 31)).astype(np.uint32)
+    planes = np.ascontiguousarray(Z.T).view(np.uint8).reshape(3, -1, 4).transpose(0, 2, 1)
+    blob = lzma.compress(np.ascontiguousarray(planes).tobytes(), preset=9)
+    return np.frombuffer(blob, dtype=np.uint8), s
+
+
+def save_large_cloud_fixture(name, X_fix, X_mov):
+    fb, fs = encode_cloud(X_fix)
+    mb, ms = encode_cloud(X_mov)
+    np.savez(GOLD / f"data_{name}.npz", codec=np.array("delta-zigzag-byteplane-lzma"),
+             fix_blob=fb, mov_blob=mb, n_fix=np.int64(len(X_fix)), n_mov=np.int64(len(X_mov)),
+             fix_scale=np.int64(fs), mov_scale=np.int64(ms))
+
+
+def read_xyz(path):
+    import pandas as pd
+
+    X = pd.read_csv(path, sep=r"\s+", header=None).to_numpy(dtype=np.float64)
+    G = np.genfromtxt(path, max_rows=2000)  # the reference's reader on a sample: same doubles
+    assert np.array_equal(G, X[: len(G)])
+    return X
+
+
+def capture_debug(name, X_fix, X_mov, kwargs):
+    """Run the unmodified reference with debug_dirpath and keep a compact description of every
+    file it writes (simpleicp.py:141-143, 189-221, 317-320; corrpts.py:213-237;
+    pointcloud.py:219-226): name, header line, row count, first and last text lines, column sums,
+    and the full numeric content of the correspondence dumps."""
+    import tempfile
+
+    import logging
+
+    out = {}
+    lines = []
+
+    class Grab(logging.Handler):
+        def emit(self, record):
+            lines.append(record.getMessage())
+
+    grab = Grab()
+    ref_log = logging.getLogger("simpleicp")
+    ref_log.addHandler(grab)
+    ref_log.setLevel(logging.INFO)
+    with tempfile.TemporaryDirectory() as td:
+        pc_fix = PointCloud(X_fix, columns=["x", "y", "z"])
+        pc_mov = PointCloud(X_mov, columns=["x", "y", "z"], copy=True)
+        icp = SimpleICP(verbose=False)
+        icp.add_point_clouds(pc_fix, pc_mov)
+        try:
+            icp.run(debug_dirpath=td, **kwargs)
+        finally:
+            ref_log.removeHandler(grab)
+        out["log_lines"] = np.array([ln.replace(td, "<debug_dir>") for ln in lines])
+        names = sorted(p.name for p in Path(td).iterdir())
+        out["names"] = np.array(names)
+        for nm in names:
+            lines = (Path(td) / nm).read_text().splitlines()
+            key = nm.replace(".", "_")
+            out[f"{key}__header"] = np.array(lines[0])
+            out[f"{key}__rows"] = np.int64(len(lines) - 1)
+            out[f"{key}__head"] = np.array(lines[1:4])
+            out[f"{key}__tail"] = np.array(lines[-1])
+            data = np.loadtxt(Path(td) / nm, comments="//")
+            out[f"{key}__colsum"] = data.sum(axis=0)
+            if "correspondences" in nm:
+                out[f"{key}__data"] = data
+    np.savez_compressed(GOLD / f"debug_{name}.npz", **out)
+    print(f"{name}: debug dump captured, {len(names)} files")
+
+
 def capture(name, file1, file2, kwargs):
-    X_fix = np.genfromtxt(REF / "data" / file1)
-    X_mov = np.genfromtxt(REF / "data" / file2)
+    if name in TRAVEL_LARGE:
+        X_fix, X_mov = read_xyz(REF / "data" / file1), read_xyz(REF / "data" / file2)
+        save_large_cloud_fixture(name, X_fix, X_mov)
+    else:
+        X_fix = np.genfromtxt(REF / "data" / file1)
+        X_mov = np.genfromtxt(REF / "data" / file2)
     if name in TRAVEL:
         save_cloud_fixture(name, X_fix, X_mov)
+    if name in DEBUG_DUMPS:
+        capture_debug(name, X_fix, X_mov, kwargs)
+    if "--fixtures-only" in sys.argv:
+        return
 
     rec = {"it_pc2_idx": [], "it_dist": [], "it_kept_pc1": [], "it_x": [], "it_res_stats": [],
            "it_w": []}
@@ -186,6 +282,6 @@ def capture(name, file1, file2, kwargs):
 
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    names = sys.argv[1:] or list(CONFIGS)
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(CONFIGS)
     for nm in names:
         capture(nm, *CONFIGS[nm])

@@ -52,6 +52,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
         return LIB
     nvcc = _nvcc()
+    # several ranks / threads importing a fresh checkout must not write the same objects at once
+    import fcntl
+
+    with open(OBJ / "build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
+            return LIB  # another process built it while we waited
+        return _build_locked(nvcc, dig, stamp, verbose)
+
+
+def _build_locked(nvcc: str, dig: str, stamp: Path, verbose: bool) -> Path:
 
     def compile_one(src: str):
         obj = OBJ / (src.rsplit(".", 1)[0] + ".o")

@@ -17,6 +17,7 @@ LIB_PATH = PKG / "libsicp_b200.so"
 
 SICP_OK, SICP_ERR_BAD_ARG, SICP_ERR_NO_OVERLAP, SICP_ERR_TOO_FEW_CORR = 0, 1, 2, 3
 SICP_ERR_CUDA, SICP_ERR_SINGULAR, SICP_ERR_STATE = 4, 5, 6
+ABI_VERSION = 2  # include/sicp_b200.h: SICP_ABI_VERSION
 NN_AUTO, NN_GRID, NN_BRUTE = 0, 1, 2
 SIGN_DGEEV, SIGN_CANONICAL = 0, 1
 
@@ -88,15 +89,27 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             raise ImportError(f"SICP_B200_LIB={override} does not exist")
     else:
         lib_path = LIB_PATH
-    if not override and not LIB_PATH.exists():
-        if not build_if_missing:
-            raise ImportError(f"{LIB_PATH} is missing; run `python -m simpleicp_b200._build`")
-        from . import _build
+    if not override:
+        if build_if_missing:
+            # digest-checked and cheap when up to date: a library left over from older sources is
+            # rebuilt instead of being loaded against newer ctypes struct layouts.  Where nvcc is
+            # absent (a box that only received the built .so) the existing library is used and the
+            # ABI version check below is the guard.
+            from . import _build
 
-        _build.build()
+            try:
+                _build.build()
+            except RuntimeError:
+                if not LIB_PATH.exists():
+                    raise ImportError(f"{LIB_PATH} is missing and cannot be built (nvcc not found)")
+        elif not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} is missing; run `python -m simpleicp_b200._build`")
     lib = C.CDLL(str(lib_path))
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.sicp_abi_version.restype = i32
+    if lib.sicp_abi_version() != ABI_VERSION:
+        raise ImportError(f"{lib_path} has ABI version {lib.sicp_abi_version()}, this binding needs "
+                          f"{ABI_VERSION}: rebuild with `python -m simpleicp_b200._build --force`")
     lib.sicp_last_error.restype = C.c_char_p
     lib.sicp_last_error.argtypes = [vp]
     sigs = {
@@ -214,6 +227,17 @@ def current_stream_ptr(device: int) -> int:
     return 0
 
 
+def current_device() -> int:
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except ImportError:
+        pass
+    return 0
+
+
 def pinned_empty(shape, dtype) -> np.ndarray:
     """Host output buffer in pinned memory (through torch) so D2H copies run at link speed."""
     try:
@@ -252,6 +276,14 @@ class Engine:
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.sicp_destroy(self._h)
             self._h = C.c_void_p()
+
+    @property
+    def alive(self) -> bool:
+        return bool(getattr(self, "_h", None))
+
+    def reset_options(self):
+        """Back to the library defaults (used when a cached engine is handed out again)."""
+        self._check(self._lib.sicp_set_option(self._h, b"defaults", 0.0))
 
     def __del__(self):
         try:

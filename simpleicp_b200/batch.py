@@ -106,6 +106,7 @@ def simpleicp_batch(
     device: int = 0,
     register_fn=None,
     concurrency: int = 4,
+    on_error: str = "raise",
     **run_kwargs,
 ) -> np.ndarray:
     """Register every pair; returns the (n_pairs, 20) record table on every rank.
@@ -116,6 +117,12 @@ def simpleicp_batch(
     the collective on CPU.  On the GPU path `concurrency` engines, each on its own CUDA stream and
     driven by its own thread (the C calls release the GIL), work through the rank's share so the
     host round trips of small registrations overlap.
+
+    A pair that cannot be registered (no overlap, fewer than 6 correspondences: ordinary
+    data-dependent outcomes) gets a NaN record whose `iterations` field is minus the library's
+    status code; every rank still takes part in the collective.  Afterwards `on_error="raise"`
+    raises BatchError (same on every rank, `.table` holds the full table, `.failed` the pair
+    numbers), `on_error="nan"` just returns the table.
     """
     if n_pairs is None:
         n_pairs = len(pairs)  # type: ignore[arg-type]
@@ -127,10 +134,22 @@ def simpleicp_batch(
         last = res.records[res.iterations - 1]
         return pack_record(res.H, res.iterations, last["n_kept"], last["mean_res"], last["std_res"])
 
+    def guarded(fn, Xf, Xm, **kw):
+        try:
+            return record(fn(Xf, Xm, **kw))
+        except Exception as e:  # noqa: BLE001 — recorded per pair, reported after the gather
+            code = getattr(getattr(e, "__cause__", None) or e, "code", None)
+            msg = str(e)
+            if code is None:
+                code = 2 if "overlap" in msg else (3 if "correspondences" in msg else 99)
+            messages.append(msg)
+            return pack_record(np.full((4, 4), np.nan), -int(code), 0, np.nan, np.nan)
+
+    messages: List[str] = []
     if register_fn is not None:
         for j, i in enumerate(mine):
             Xf, Xm = get(i)
-            local[j] = record(register_fn(Xf, Xm, **run_kwargs))
+            local[j] = guarded(register_fn, Xf, Xm, **run_kwargs)
     else:
         import threading
 
@@ -138,6 +157,7 @@ def simpleicp_batch(
 
         from .simpleicp import register
 
+        run_kwargs.setdefault("want_normals", False)  # one fused sicp_register call per pair
         n_workers = max(1, min(concurrency, len(mine)))
         errors = []
         pool = _engine_pool(device, n_workers)
@@ -153,7 +173,7 @@ def simpleicp_batch(
                         if j is None:
                             break
                         Xf, Xm = get(mine[j])
-                        local[j] = record(register(Xf, Xm, engine=eng, **run_kwargs))
+                        local[j] = guarded(register, Xf, Xm, engine=eng, **run_kwargs)
             except Exception as e:  # surfaced after the join
                 errors.append(e)
 
@@ -162,11 +182,28 @@ def simpleicp_batch(
             t.start()
         for t in threads:
             t.join()
-        if errors:
-            raise errors[0]
+        if errors:  # not a per-pair outcome (bad generator, lost device): NaN for what is missing
+            messages.append(repr(errors[0]))
+            done = np.isfinite(local[:, 16]) & (local[:, 16] != 0)
+            local[~done] = pack_record(np.full((4, 4), np.nan), -99, 0, np.nan, np.nan)
     dev = None
     if dist is not None and world_size > 1:
         import torch
 
         dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
-    return gather_records(local, n_pairs, world_size, rank, dist, dev)
+    table = gather_records(local, n_pairs, world_size, rank, dist, dev)
+    failed = np.flatnonzero(table[:, 16] < 0)
+    if failed.size and on_error == "raise":
+        raise BatchError(table, failed, messages)
+    return table
+
+
+class BatchError(RuntimeError):
+    """Some pairs of a batch could not be registered; `.table` is the complete record table."""
+
+    def __init__(self, table, failed, messages):
+        codes = sorted({int(-table[i, 16]) for i in failed})
+        super().__init__(f"{len(failed)} of {len(table)} pairs failed (pairs {failed[:8].tolist()}"
+                         f"{' ...' if len(failed) > 8 else ''}, status codes {codes})"
+                         + (f"; first local message: {messages[0]}" if messages else ""))
+        self.table, self.failed, self.messages = table, failed, messages

@@ -248,7 +248,18 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
   API_BEGIN(ctx)
   SICP_REQUIRE(key != nullptr, SICP_ERR_BAD_ARG, "key is NULL");
   const std::string k(key);
-  if (k == "nn_engine") {
+  if (k == "defaults") {
+    const Ctx d;  // the member initialisers are the defaults
+    c.nn_engine = d.nn_engine;
+    c.sign_mode = d.sign_mode;
+    c.variant = d.variant;
+    c.grid_target_occ = d.grid_target_occ;
+    c.grid_max_rings = d.grid_max_rings;
+    c.grid_sort_cells = d.grid_sort_cells;
+    c.rs_blocks = d.rs_blocks;
+    c.match_group = d.match_group;
+    c.host_sync_every = d.host_sync_every;
+  } else if (k == "nn_engine") {
     SICP_REQUIRE(value == 0 || value == 1 || value == 2, SICP_ERR_BAD_ARG, "nn_engine must be 0, 1 or 2");
     c.nn_engine = (int)value;
   } else if (k == "sign_mode") {

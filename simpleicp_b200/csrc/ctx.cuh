@@ -114,6 +114,7 @@ struct Ctx {
   DevBuf<unsigned int> lin_hist;          // predictor histogram (match kernels -> reject kernel)
   bool lin_hist_pending = false;          // filled by a match, not yet consumed by a reject
   bool lin_hist_init = false;
+  bool bf_attr_set = false;               // k_bf_nn's dynamic shared memory limit raised on this device
   sicp_iter_record* rec_host = nullptr;  // pinned
   double* scal_host = nullptr;           // pinned staging for small reads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

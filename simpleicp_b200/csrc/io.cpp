@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,7 +33,19 @@ inline const char* skip_ws(const char* p, const char* e) {
   return p;
 }
 
+void parse_chunk_impl(Chunk& c);
+
+// runs inside std::thread: an exception escaping it would call std::terminate
 void parse_chunk(Chunk& c) {
+  try {
+    parse_chunk_impl(c);
+  } catch (...) {
+    c.xyz.clear();
+    c.bad_line = -2;  // out of memory
+  }
+}
+
+void parse_chunk_impl(Chunk& c) {
   const char* p = c.b;
   long long line = 0;
   c.xyz.reserve((size_t)(c.e - c.b) / 24 * 3 + 3);
@@ -69,6 +82,8 @@ extern "C" {
 
 const char* sicp_io_last_error(void) { return g_io_error.c_str(); }
 
+static int32_t xyz_load_impl(const char* path, double** xyz, int64_t* n);
+
 int32_t sicp_xyz_load(const char* path, double** xyz, int64_t* n) {
   if (!path || !xyz || !n) {
     g_io_error = "NULL argument";
@@ -76,6 +91,15 @@ int32_t sicp_xyz_load(const char* path, double** xyz, int64_t* n) {
   }
   *xyz = nullptr;
   *n = 0;
+  try {
+    return xyz_load_impl(path, xyz, n);
+  } catch (const std::exception& e) {  // nothing may unwind through the C boundary
+    g_io_error = std::string("reading ") + path + ": " + e.what();
+    return SICP_ERR_BAD_ARG;
+  }
+}
+
+static int32_t xyz_load_impl(const char* path, double** xyz, int64_t* n) {
   FILE* f = fopen(path, "rb");
   if (!f) {
     g_io_error = std::string("cannot open ") + path;
@@ -100,6 +124,7 @@ int32_t sicp_xyz_load(const char* path, double** xyz, int64_t* n) {
   const char* cur = base;
   for (int t = 0; t < nt; ++t) {
     const char* stop = (t == nt - 1) ? end : base + size * (t + 1) / nt;
+    if (stop < cur) stop = cur;  // a line longer than a whole share: the earlier chunk took it
     while (stop < end && *stop != '\n') ++stop;
     if (stop < end) ++stop;
     chunks[(size_t)t].b = cur;
@@ -112,6 +137,10 @@ int32_t sicp_xyz_load(const char* path, double** xyz, int64_t* n) {
   for (auto& x : th) x.join();
   size_t total = 0;
   for (auto& c : chunks) {
+    if (c.bad_line == -2) {
+      g_io_error = std::string("out of memory while parsing ") + path;
+      return SICP_ERR_BAD_ARG;
+    }
     if (c.bad_line >= 0) {
       g_io_error = std::string("malformed line in ") + path + " (need three numbers per line)";
       return SICP_ERR_BAD_ARG;

@@ -633,10 +633,10 @@ void gather_queries_launch(Ctx& c) {
 
 // Brute-force pass over either the unresolved list (qlist != nullptr) or all K queries.
 static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute belongs to the (device-specific) function handle: once per context, not per process
+  if (!c.bf_attr_set) {
     SICP_CUDA(cudaFuncSetAttribute(k_bf_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBfSmem));
-    attr_set = true;
+    c.bf_attr_set = true;
   }
   const long long n_tiles = (c.n_mov + BF_TILE - 1) / BF_TILE;
   SICP_REQUIRE(c.mov_f4.cap >= (size_t)n_tiles * BF_TILE, SICP_ERR_STATE,

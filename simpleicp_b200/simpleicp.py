@@ -71,6 +71,46 @@ def _change(new: float, old: float) -> float:
     return np.abs((new - old) / old * 100)
 
 
+# One engine (CUDA context state, stream, ~250 MB of device buffers at 1M-point clouds) per
+# (device, thread) is kept for calls that do not bring their own: creating and destroying it per
+# call costs more than a small registration.  Engines are not thread-safe, hence the thread key.
+_DEFAULT_ENGINES: dict = {}
+
+
+def default_engine(device: Optional[int] = None) -> _capi.Engine:
+    import threading
+
+    if device is None:
+        device = _capi.current_device()
+    key = (int(device), threading.get_ident())
+    eng = _DEFAULT_ENGINES.get(key)
+    if eng is None or not eng.alive:
+        eng = _capi.Engine(int(device))
+        _DEFAULT_ENGINES[key] = eng
+    else:
+        eng.reset_options()
+    return eng
+
+
+def close_default_engines() -> None:
+    """Release the engines kept for register()/simpleicp()/SimpleICP.run calls without `engine=`."""
+    for eng in list(_DEFAULT_ENGINES.values()):
+        eng.close()
+    _DEFAULT_ENGINES.clear()
+
+
+import atexit as _atexit  # noqa: E402
+
+_atexit.register(close_default_engines)
+
+
+def _host_xyz(X) -> np.ndarray:
+    """Host float64 view of a cloud given as NumPy array or (CUDA) torch tensor."""
+    if hasattr(X, "detach"):
+        X = X.detach().cpu().numpy()
+    return np.asarray(X, dtype=np.float64)
+
+
 class _Result:
     """Everything one registration produces."""
 
@@ -138,11 +178,10 @@ def register(
     H0 = mathutils.create_homogeneous_transformation_matrix(
         mathutils.euler_angles_to_rotation_matrix(obs[0], obs[1], obs[2]), obs[3:]
     )
-    own = engine is None
-    eng = engine or _capi.Engine()
+    eng = engine if engine is not None else default_engine()
     fused = (idx_selected is None and normals is None and not stepwise and on_normals is None
              and not want_normals)
-    try:
+    try:  # noqa: PLR1702
         if fused:
             # the whole of SimpleICP.run as one library call: nothing but the clouds goes in,
             # nothing but the results comes back (simpleicp_b200/_capi.py::register_fused)
@@ -190,7 +229,7 @@ def register(
         try:
             if stepwise:
                 out = _loop_stepwise(eng, params, obs, w_obs, distance_weights, min_planarity,
-                                     min_change, max_iterations, debug_dirpath, X_fix, idx)
+                                     min_change, max_iterations, debug_dirpath, X_fix, X_mov, idx)
             else:
                 out = _loop_fused(eng, params)
         except _capi.SicpError as e:
@@ -203,18 +242,18 @@ def register(
 
         X_t = eng.transform(H, out=transform_out)
         if debug_dirpath:
-            pointcloud.PointCloud(np.asarray(X_t), columns=["x", "y", "z"]).write_xyz(
-                Path(debug_dirpath).joinpath(f"iteration{iterations - 1:03d}_postoptim_pcmov.xyz")
-            )
+            _capi.write_xyz(Path(debug_dirpath).joinpath(f"iteration{iterations - 1:03d}_postoptim_pcmov.xyz"),
+                            _host_xyz(X_t))
         r = _Result()
         r.H, r.X_mov_transformed, r.rbp, r.residuals = H, X_t, rbp, residuals
         r.idx_selected, r.normals, r.records = idx, nrm, records
         r.iterations, r.converged, r.loop_ms = iterations, converged, loop_ms
         r.timings = eng.timings()
         return r
-    finally:
-        if own:
-            eng.close()
+    except _capi.SicpError as e:
+        if e.code == _capi.SICP_ERR_CUDA and engine is None:
+            eng.close()  # do not keep a context whose device state is unknown
+        raise
 
 
 def _records(log):
@@ -281,7 +320,7 @@ def _register_fused(eng, X_fix, X_mov, correspondences, neighbors, min_planarity
 
 
 def _loop_stepwise(eng, params, obs, w_obs, distance_weights, min_planarity, min_change,
-                   max_iterations, debug_dirpath, X_fix, idx):
+                   max_iterations, debug_dirpath, X_fix, X_mov, idx):
     """The same loop driven stage by stage through sicp_match / sicp_reject / sicp_solve; used
     for debug dumps (reference: simpleicp.py:141-143, 189-200, 216-221) and by the tests to check
     the fused loop against its parts."""
@@ -294,13 +333,14 @@ def _loop_stepwise(eng, params, obs, w_obs, distance_weights, min_planarity, min
     converged = False
     t0 = time.perf_counter()
     it = -1
+    dbg = _DebugWriter(debug_dirpath, X_fix, X_mov, idx) if debug_dirpath else None
     for it in range(max_iterations):
+        if dbg:
+            dbg.preoptim_clouds(eng, it, H)
         pc2_idx, d = eng.match(H)
-        if debug_dirpath:
-            _write_debug_preoptim(eng, debug_dirpath, it, H, X_fix, idx)
         keep, n_kept, st = eng.reject(min_planarity)
-        if debug_dirpath and n_kept:
-            _write_debug_corr(eng, debug_dirpath, it, H, X_fix, idx, pc2_idx, d, keep)
+        if dbg and n_kept >= 6:  # the reference raises before writing (simpleicp.py:209-221)
+            dbg.correspondences(it, pc2_idx, d, keep)
         x, H, residuals, rs, w_used = eng.solve(x, obs, w_obs, w, n_kept)
         if w is None:
             w = w_used  # frozen after iteration 0 (simpleicp.py:229-234)
@@ -316,25 +356,30 @@ def _loop_stepwise(eng, params, obs, w_obs, distance_weights, min_planarity, min
     return x, sigma, H, residuals, records, it + 1, converged, (time.perf_counter() - t0) * 1e3
 
 
-def _write_debug_preoptim(eng, dirpath, it, H, X_fix, idx):
-    d = Path(dirpath)
-    if it == 0:
-        pointcloud.PointCloud(np.asarray(X_fix), columns=["x", "y", "z"]).write_xyz(
-            d.joinpath(f"iteration{it:03d}_preoptim_pcfix.xyz")
-        )
-    pointcloud.PointCloud(np.asarray(eng.transform(H)), columns=["x", "y", "z"]).write_xyz(
-        d.joinpath(f"iteration{it:03d}_preoptim_pcmov.xyz")
-    )
+class _DebugWriter:
+    """The reference's per-iteration debug files (simpleicp.py:189-221, corrpts.py:213-237,
+    pointcloud.py:219-226).  The movable cloud is transformed ONCE per iteration (the file
+    contains all of it); the correspondence dump takes its movable coordinates from the
+    caller's UNTRANSFORMED cloud — the reference writes it after pc2.transform_by_H(inv(H))."""
 
+    def __init__(self, dirpath, X_fix, X_mov, idx):
+        self.dir = Path(dirpath)
+        self.X_fix = _host_xyz(X_fix)
+        self.X_mov = _host_xyz(X_mov)
+        self.idx = idx
 
-def _write_debug_corr(eng, dirpath, it, H, X_fix, idx, pc2_idx, dist, keep):
-    # reference: CorrPts.write_xyz (corrpts.py:213-237)
-    X2 = np.asarray(eng.transform(H))
-    P1 = np.asarray(X_fix)[idx[keep]]
-    P2 = X2[pc2_idx[keep]]
-    np.savetxt(Path(dirpath).joinpath(f"iteration{it:03d}_preoptim_correspondences.xyz"),
-               np.column_stack((P1, P2, dist[keep])), delimiter=" ",
-               header="X1 Y1 Z1 X2 Y2 Z2 point_to_plane_distance", comments="//")
+    def preoptim_clouds(self, eng, it, H):
+        if it == 0:
+            _capi.write_xyz(self.dir.joinpath(f"iteration{it:03d}_preoptim_pcfix.xyz"), self.X_fix)
+        _capi.write_xyz(self.dir.joinpath(f"iteration{it:03d}_preoptim_pcmov.xyz"),
+                        np.asarray(eng.transform(H)))
+
+    def correspondences(self, it, pc2_idx, dist, keep):
+        P1 = self.X_fix[self.idx[keep]]
+        P2 = self.X_mov[pc2_idx[keep]]
+        np.savetxt(self.dir.joinpath(f"iteration{it:03d}_preoptim_correspondences.xyz"),
+                   np.column_stack((P1, P2, dist[keep])), delimiter=" ",
+                   header="X1 Y1 Z1 X2 Y2 Z2 point_to_plane_distance", comments="//")
 
 
 def _log_run(records, iterations, converged, H, rbp) -> None:
@@ -407,15 +452,24 @@ class SimpleICP:
             if not have:
                 pc1.set_normals(idx, *nrm)
 
+        # the reference matches against the SELECTED movable points only (corrpts.py:131-135);
+        # the final transform moves all of them (simpleicp.py:316)
+        X2 = pc2.X
+        sel2 = pc2["selected"].to_numpy(dtype=bool)
+        X2_search = X2 if sel2.all() else np.ascontiguousarray(X2[sel2])
+
         res = register(
-            pc1.X, pc2.X, correspondences=correspondences, neighbors=neighbors,
+            pc1.X, X2_search, correspondences=correspondences, neighbors=neighbors,
             min_planarity=min_planarity, max_overlap_distance=max_overlap_distance,
             min_change=min_change, max_iterations=max_iterations, distance_weights=distance_weights,
             rbp_observed_values=rbp_observed_values, rbp_observation_weights=rbp_observation_weights,
             debug_dirpath=debug_dirpath, idx_selected=idx0, normals=normals, on_normals=store_normals,
         )
         pc1.idx_selected = res.idx_selected
-        pc2._set_xyz(np.asarray(res.X_mov_transformed))
+        if sel2.all():
+            pc2._set_xyz(np.asarray(res.X_mov_transformed))
+        else:
+            pc2._set_xyz(X2 @ res.H[:3, :3].T + res.H[:3, 3])
         _log.info(f"Finished in {time.time() - start_time:.3f} seconds!")
         return res.H, pc2.X, res.rbp, res.residuals
 

@@ -29,7 +29,7 @@ def test_header_symbols_exported():
     lib = _capi.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sicp_abi_version() == 1
+    assert lib.sicp_abi_version() == _capi.ABI_VERSION
 
 
 def test_struct_layouts_match_header(tmp_path):

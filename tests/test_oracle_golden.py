@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import REFERENCE, load_golden, load_pair
+from conftest import load_golden, load_pair
 from oracle import simpleicp_oracle as O
 
 
@@ -61,11 +61,21 @@ def test_oracle_errors():
         O.simpleicp(X_fix, X_mov, rbp_observation_weights=(np.inf,) * 6)
 
 
-@pytest.mark.skipif(not REFERENCE.exists(), reason="large lidar inputs only exist in the build container")
-@pytest.mark.parametrize("name,f1,f2", [("airborne", "airborne_lidar1", "airborne_lidar2")])
-def test_oracle_large_lidar(name, f1, f2):
+@pytest.mark.parametrize("name", ["airborne", "terrestrial"])
+def test_oracle_large_lidar(name):
+    """The two 1.3 M-point lidar pairs of the reference's test file
+    (python/simpleicp/tests/test_simpleicp.py:44-63), inputs from the compressed fixtures:
+    the restatement reproduces every stage of the unmodified reference bit for bit."""
     g = load_golden(name)
-    X_fix = np.genfromtxt(REFERENCE / "data" / f"{f1}.xyz")
-    X_mov = np.genfromtxt(REFERENCE / "data" / f"{f2}.xyz")
-    H, *_ = O.simpleicp(X_fix, X_mov, **g["kwargs"])
+    X_fix, X_mov = load_pair(name)
+    assert X_fix.shape[0] == int(g["n_fix"]) and X_mov.shape[0] == int(g["n_mov"])
+    tr = O.Trace()
+    H, X_t, x, sigma, res = O.simpleicp(X_fix, X_mov, trace=tr, **g["kwargs"])
+    assert len(tr.iterations) == g["it_x"].shape[0]
+    assert np.array_equal(tr.idx_sel, g["idx_sel"])
+    assert np.array_equal(tr.normals, g["normals"])
+    for i, it in enumerate(tr.iterations):
+        assert np.array_equal(it.pc2_idx, g["it_pc2_idx"][i])
+        assert np.array_equal(it.keep, g["it_keep"][i])
     np.testing.assert_allclose(H, g["H"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(res, g["residuals"], rtol=0, atol=1e-13)
