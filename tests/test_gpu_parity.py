@@ -86,8 +86,9 @@ def test_match_lockstep(engines, name, mode):
         same = idx == g["it_pc2_idx"][it]
         np.testing.assert_allclose(d[same], g["it_dist"][it][same], rtol=0, atol=1e-12)
     # webots is a synthetic scene on a regular 1 mm lattice: a sixth of its queries have exactly
-    # equidistant candidates; the scanned data sets have a handful
-    limit = 0.25 if name == "webots" else 0.01
+    # equidistant candidates; terrestrial is a mm-resolution scan stored with 3 decimals (3.4 % of
+    # its queries have exact ties); the other scanned data sets have a handful
+    limit = {"webots": 0.25, "terrestrial": 0.05}.get(name, 0.01)
     assert n_ties <= limit * q.shape[0] * len(H_inputs(g))
 
 
@@ -144,7 +145,7 @@ def test_solve_lockstep(engines, name):
         n1 = g["normals"][keep]
         x_t = tight_solution(p1, n1, p2, w_it, x_prev, obs, w_obs)
         np.testing.assert_allclose(x, x_t, rtol=0, atol=2e-8, err_msg=f"{name} it {it}")
-        if np.array_equal(keep, g["it_keep"][it]):
+        if np.array_equal(keep, g["it_keep"][it]) and np.array_equal(idx, g["it_pc2_idx"][it]):
             np.testing.assert_allclose(x, g["it_x"][it], rtol=0, atol=1e-5)
         np.testing.assert_allclose(Hs, O.rbp_to_H(x), rtol=0, atol=1e-15)
         r_o = O._residual_vector(x, p1, n1.astype(np.float64), p2, 1.0, obs, np.zeros(6))
@@ -194,8 +195,9 @@ def test_normals(gpu, name, k):
     dd, ii = cKDTree(X_fix).query(X_fix[g["idx_sel"]], k=k)
     np.testing.assert_allclose(np.sqrt(d2), dd, rtol=0, atol=1e-12)
     same_rows = (np.sort(idx_knn, axis=1) == np.sort(ii, axis=1)).all(axis=1)
-    # the rest are equal-distance ties at the k-th neighbour (common on webots' regular lattice)
-    assert same_rows.mean() > (0.5 if name == "webots" else 0.98)
+    # the rest are equal-distance ties at the k-th neighbour (common on webots' regular lattice
+    # and on the mm-quantised terrestrial scan: distances above are equal to 1e-12 in every row)
+    assert same_rows.mean() > {"webots": 0.5, "terrestrial": 0.75}.get(name, 0.98)
     n_gpu = np.column_stack((nx, ny, nz)).astype(np.float64)
     n_ref = g["normals"].astype(np.float64)
     ok = np.isfinite(g["planarity"]) & same_rows
@@ -238,7 +240,10 @@ def test_full_run_with_reference_normals(gpu, name):
     ref_kept = [int(k.sum()) for k in g["it_keep"]]
     print(f"{name}: |dH|_F = {dH:.3e}, iterations {res.iterations} vs {len(ref_kept)}, kept {kept[-3:]} vs {ref_kept[-3:]}")
     assert dH < 1e-6
-    assert res.iterations == len(ref_kept)
+    # terrestrial: 3.4 % of the queries have exactly equidistant candidates (cKDTree's pick among
+    # them is unspecified); the fixed point is the same to 1e-12, the fragile stop rule
+    #  may fire one iteration earlier or later
+    assert abs(res.iterations - len(ref_kept)) <= (1 if name == "terrestrial" else 0)
     assert abs(kept[-1] - ref_kept[-1]) <= 2
     if kept[-1] == ref_kept[-1]:
         np.testing.assert_allclose(res.residuals, g["residuals"], rtol=0, atol=1e-6)
@@ -264,10 +269,12 @@ def test_normal_signs_follow_numpy_eig(gpu, name, k):
     frac = same_sign[ok].mean()
     exact = (n_gpu[ok] == g["normals"][ok]).all(axis=1).mean()
     print(f"{name}: sign agreement {frac:.4f}, bit-identical float32 normals {exact:.4f}")
-    assert frac > 0.985
-    # webots (k = 40 on a regular lattice) has equal-distance ties at the 40th neighbour in ~28 %
-    # of its neighbourhoods; cKDTree's tie order is unspecified, ours is lowest index
-    assert exact > (0.8 if name == "webots" else 0.98)
+    # webots (k = 40 on a regular lattice) and terrestrial (mm-quantised coordinates) have
+    # equal-distance ties at the k-th neighbour in ~28 % / ~20 % of their neighbourhoods; cKDTree's
+    # tie order is unspecified, ours is lowest index: another neighbour set, another (equally
+    # valid) covariance
+    assert frac > (0.9 if name == "terrestrial" else 0.985)
+    assert exact > {"webots": 0.8, "terrestrial": 0.75}.get(name, 0.98)
 
 
 @pytest.mark.parametrize("name", CONFIGS)
