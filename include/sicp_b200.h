@@ -85,7 +85,9 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value);
  *        brute-force pass takes over, default 8), "grid_sort_cells" (0/1), "host_sync_every"
  *        (iterations queued between host reads in sicp_run, default 4), "match_group" (lanes per
  *        query in the grid search: 0 = by K, 1, 4, 8, 16), "rs_blocks" (blocks of the cooperative
- *        reject/solve kernel, 0 = one per SM)                                                  */
+ *        reject/solve kernel, 0 = one per SM), "fused" (1: iterations after the first run their
+ *        reject + solve in the barrier-free kernel, 0: always the cooperative kernel),
+ *        "defaults" (any value: every option back to its default)                              */
 
 /* ---- clouds: SimpleICP.add_point_clouds (simpleicp.py:58-73) + PointCloud.X ---------------- */
 int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz /*[h|d] n_fix x 3*/, int64_t n_fix,
@@ -226,6 +228,10 @@ typedef struct {
   double upload_ms, grid_mov_ms, grid_fix_ms, overlap_ms, normals_ms, match_ms, reject_solve_ms,
       transform_ms;
   int64_t kernel_launches; /* kernels of this library launched on this context so far           */
+  int64_t fused_iterations; /* last sicp_run / sicp_register: iterations whose reject + solve ran
+                               in the barrier-free kernel (all but the first, normally)          */
+  int64_t rerun_iterations; /* ... iterations repeated through the general kernel because the
+                               order-statistic prediction of the barrier-free kernel missed       */
 } sicp_timings;
 int32_t sicp_get_timings(sicp_ctx* ctx, sicp_timings* t /*[h]*/);
 
@@ -240,7 +246,10 @@ int32_t sicp_time_stages(sicp_ctx* ctx, const sicp_run_params* p, int32_t reps, 
  * relative to kernel entry.  [1] median done, [2] MAD done, [3] moments accumulated, [4] grid
  * barrier passed, [5] LM solve done, [6] barrier, [7] residual pass, [8] barrier, [9] exit;
  * [10..12] / [14..16] radix levels done / gather barrier / sort done for the median / MAD;
- * [24],[25] radix levels used, [26],[27] candidates sorted (raw counts, not times).            */
+ * [24],[25] radix levels used, [26],[27] candidates sorted (raw counts, not times); [28] path:
+ * 0 radix select, 1 predictor histogram (cooperative kernel), 2 barrier-free kernel (there
+ * [2] = select done, [3] = accumulation done in block 0, [4] = last block starts, [17] partials
+ * reduced, [18] M assembled, [19] solve done, [9] exit).                                        */
 int32_t sicp_get_phase_times(sicp_ctx* ctx, double us[32] /*[h]*/);
 
 /* ---- .xyz text I/O (host only; SURVEY.md section 8f: file parsing dominates end-to-end time on

@@ -64,7 +64,9 @@ class RunResult(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("upload_ms", "grid_mov_ms", "grid_fix_ms", "overlap_ms",
                                           "normals_ms", "match_ms", "reject_solve_ms",
-                                          "transform_ms")] + [("kernel_launches", C.c_int64)]
+                                          "transform_ms")] + [("kernel_launches", C.c_int64),
+                                                            ("fused_iterations", C.c_int64),
+                                                            ("rerun_iterations", C.c_int64)]
 
 
 class SicpError(RuntimeError):

@@ -127,6 +127,26 @@ void require_normals(Ctx& c) {
                "normals are missing: call sicp_estimate_normals or sicp_set_normals first");
 }
 
+// One iteration's launches: match, then the barrier-free reject/solve kernel when the previous
+// iteration of this run left a predictor (it > 0), else the general cooperative kernel.
+void launch_iteration(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, int rec_slot,
+                      bool allow_fused, bool want_sigma, cudaEvent_t mid = nullptr, cudaEvent_t after_match = nullptr) {
+  match_launch(c, true, nullptr, mid, c.expect_unresolved);
+  if (after_match) SICP_CUDA(cudaEventRecord(after_match, c.stream));
+  if (allow_fused && c.fused && it > 0)
+    rs_fused_launch(c, p, it, arm_stop, rec_slot, want_sigma);
+  else
+    reject_solve_launch(c, p, it, true, arm_stop, rec_slot);
+}
+
+// The fused kernel found its prediction unusable and parked the pipeline (state.stop == 3):
+// clear the flag so that the iteration can be repeated with the general kernel.
+void clear_stop_flag(Ctx& c) {
+  static const int zero = 0;
+  SICP_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(c.dev_state.p) + offsetof(DevState, stop), &zero,
+                            sizeof(int), cudaMemcpyHostToDevice, c.stream));
+}
+
 void fetch_records(Ctx& c, int first, int count) {
   SICP_CUDA(cudaMemcpyAsync(c.rec_host + first, c.ws.rec.p + first, sizeof(sicp_iter_record) * count,
                             cudaMemcpyDeviceToHost, c.stream));
@@ -259,6 +279,7 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.rs_blocks = d.rs_blocks;
     c.match_group = d.match_group;
     c.host_sync_every = d.host_sync_every;
+    c.fused = d.fused;
   } else if (k == "nn_engine") {
     SICP_REQUIRE(value == 0 || value == 1 || value == 2, SICP_ERR_BAD_ARG, "nn_engine must be 0, 1 or 2");
     c.nn_engine = (int)value;
@@ -276,6 +297,8 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.grid_max_rings = (int)value;
   } else if (k == "grid_sort_cells") {
     c.grid_sort_cells = (value != 0) ? 1 : 0;
+  } else if (k == "fused") {
+    c.fused = (value != 0) ? 1 : 0;
   } else if (k == "rs_blocks") {
     SICP_REQUIRE(value >= 0 && value <= 256, SICP_ERR_BAD_ARG, "rs_blocks out of range");
     c.rs_blocks = (int)value;
@@ -549,16 +572,23 @@ int32_t sicp_iterate(sicp_ctx* ctx, const sicp_run_params* p, const double x_in[
     ctx->it_counter = 0;
   }
   if (x_in) c.expect_unresolved = true;
-  match_launch(c, true, nullptr, nullptr, c.expect_unresolved);
-  reject_solve_launch(c, *p, ctx->it_counter, true, false, 0);
-  ctx->it_counter++;
+  launch_iteration(c, *p, ctx->it_counter, false, 0, true, false);
   c.matched = c.rejected = true;
   if (rec) {
+    DevState h;
     fetch_records(c, 0, 1);
+    SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
     sync(c);
+    if (h.stop == 3) {  // prediction unusable: the same iteration through the general kernel
+      clear_stop_flag(c);
+      launch_iteration(c, *p, ctx->it_counter, false, 0, false, false);
+      fetch_records(c, 0, 1);
+      sync(c);
+    }
     *rec = c.rec_host[0];
     c.expect_unresolved = rec->n_bruteforce > 0;
   }
+  ctx->it_counter++;
   API_END
 }
 
@@ -600,27 +630,41 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
   SICP_CUDA(cudaEventCreate(&e0));
   SICP_CUDA(cudaEventCreate(&e1));
   SICP_CUDA(cudaEventRecord(e0, c.stream));
-  int done = 0, fetched = 0, converged = 0;
+  int done = 0, fetched = 0, converged = 0, n_fused = 0, n_rerun = 0;
   DevState h;
   // host reads: after each of the first two iterations (they decide whether the brute-force
   // pass is still needed), then every host_sync_every iterations; the device-side stop flag turns
   // iterations queued past convergence into immediate returns
   const int every = std::max(1, c.host_sync_every);
   int next_sync = 0;
+  int general_at = -1;  // iteration to repeat with the general kernel (fused prediction missed)
   c.expect_unresolved = true;
   for (int it = 0; it < p->max_iterations; ++it) {
-    match_launch(c, true, nullptr, nullptr, c.expect_unresolved);
-    tr("match", it);
-    reject_solve_launch(c, *p, it, true, true, it);
-    tr("rs", it);
+    const bool fused = c.fused && it > 0 && it != general_at;
+    launch_iteration(c, *p, it, true, it, fused, it + 1 == p->max_iterations);
+    n_fused += fused ? 1 : 0;
+    tr(fused ? "it (fused)" : "it (general)", it);
     if (it >= next_sync || it + 1 == p->max_iterations) {
       next_sync = (it < 2) ? it + 1 : it + every;
       fetch_records(c, fetched, it + 1 - fetched);
       SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
       sync(c);
       tr("synced", it);
-      fetched = it + 1;
       done = h.iterations_done;
+      if (h.stop == 3) {
+        // the barrier-free kernel of iteration `done` could not use its prediction; everything
+        // queued behind it returned immediately.  Repeat from there with the general kernel.
+        clear_stop_flag(c);
+        SICP_CUDA(cudaMemsetAsync(c.ws.rec.p + done, 0, sizeof(sicp_iter_record) * (size_t)(it + 1 - done), c.stream));
+        n_fused -= (it + 1 - done);
+        general_at = done;
+        fetched = std::min(fetched, done);
+        it = done - 1;
+        next_sync = done;
+        ++n_rerun;
+        continue;
+      }
+      fetched = it + 1;
       c.expect_unresolved = c.rec_host[it].n_bruteforce > 0;
       if (h.stop == 2 || (done < it + 1 && !h.stop)) {
         // an iteration ended with fewer than 6 correspondences
@@ -639,9 +683,14 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
     }
   }
   SICP_CUDA(cudaEventRecord(e1, c.stream));
-  compact_residuals_launch(c);
+  // residual vector of the final iteration (reference operation order), its ordered compaction
+  // and exact two-pass statistics (they replace the moment-based values of the last record)
+  final_residuals_launch(c);
   SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  if (h.iterations_done > 0 || done > 0) fetch_records(c, std::max(done - 1, 0), 1);
   sync(c);
+  c.n_fused_last = n_fused;
+  c.n_rerun_last = n_rerun;
   tr("final", -1);
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
@@ -884,24 +933,34 @@ int32_t sicp_time_stages(sicp_ctx* ctx, const sicp_run_params* p, int32_t reps, 
   cudaEvent_t e[4];
   for (auto& ev : e) SICP_CUDA(cudaEventCreate(&ev));
   double acc[4] = {0, 0, 0, 0};
-  for (int r = 0; r < reps; ++r) {
-    if (flush_l2) SICP_CUDA(cudaMemsetAsync(c.flush_buf.p, r & 0xff, kFlushBytes, c.stream));
-    SICP_CUDA(cudaEventRecord(e[0], c.stream));
-    match_launch(c, true, nullptr, e[1], c.expect_unresolved);
-    SICP_CUDA(cudaEventRecord(e[2], c.stream));
-    reject_solve_launch(c, *p, ctx->it_counter, true, false, 0);
-    SICP_CUDA(cudaEventRecord(e[3], c.stream));
-    SICP_CUDA(cudaEventSynchronize(e[3]));
-    ctx->it_counter++;
-    float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
-    cudaEventElapsedTime(&t01, e[0], e[1]);
-    cudaEventElapsedTime(&t12, e[1], e[2]);
-    cudaEventElapsedTime(&t23, e[2], e[3]);
-    cudaEventElapsedTime(&t03, e[0], e[3]);
-    acc[0] += t01;
-    acc[1] += t12;
-    acc[2] += t23;
-    acc[3] += t03;
+  bool allow_fused = true;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int i = 0; i < 4; ++i) acc[i] = 0;
+    for (int r = 0; r < reps; ++r) {
+      if (flush_l2) SICP_CUDA(cudaMemsetAsync(c.flush_buf.p, r & 0xff, kFlushBytes, c.stream));
+      SICP_CUDA(cudaEventRecord(e[0], c.stream));
+      launch_iteration(c, *p, ctx->it_counter, false, 0, allow_fused, false, e[1], e[2]);
+      SICP_CUDA(cudaEventRecord(e[3], c.stream));
+      SICP_CUDA(cudaEventSynchronize(e[3]));
+      ctx->it_counter++;
+      float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
+      cudaEventElapsedTime(&t01, e[0], e[1]);
+      cudaEventElapsedTime(&t12, e[1], e[2]);
+      cudaEventElapsedTime(&t23, e[2], e[3]);
+      cudaEventElapsedTime(&t03, e[0], e[3]);
+      acc[0] += t01;
+      acc[1] += t12;
+      acc[2] += t23;
+      acc[3] += t03;
+    }
+    // a missed prediction parks the pipeline (every later launch returns at once): such a
+    // measurement is void — repeat it through the general kernel
+    DevState h;
+    SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    sync(c);
+    if (h.stop != 3) break;
+    clear_stop_flag(c);
+    allow_fused = false;
   }
   for (auto& ev : e) cudaEventDestroy(ev);
   for (int i = 0; i < 4; ++i) ms[i] = acc[i] / reps;
@@ -924,6 +983,8 @@ int32_t sicp_get_phase_times(sicp_ctx* ctx, double us[32]) {
 int32_t sicp_get_timings(sicp_ctx* ctx, sicp_timings* t) {
   API_BEGIN(ctx)
   SICP_REQUIRE(t != nullptr, SICP_ERR_BAD_ARG, "t is NULL");
+  c.tm.fused_iterations = c.n_fused_last;
+  c.tm.rerun_iterations = c.n_rerun_last;
   *t = c.tm;
   API_END
 }

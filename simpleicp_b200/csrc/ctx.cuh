@@ -87,6 +87,8 @@ struct Ctx {
   DevBuf<long long> nn_idx;
   DevBuf<double> dist;
   DevBuf<uint8_t> keep;
+  DevBuf<unsigned short> corr_code;  // K: predictor-histogram bin of every correspondence (match -> fused reject/solve)
+  DevBuf<double> m_xyz;              // K x 3: matched movable point, caller coordinates
   DevBuf<double> resid;          // K, valid where keep
   DevBuf<double> resid_compact;  // kept order
   DevBuf<unsigned int> unresolved;  // query ids the grid could not bound + counter at [K]
@@ -114,6 +116,10 @@ struct Ctx {
   DevBuf<unsigned int> lin_hist;          // predictor histogram (match kernels -> reject kernel)
   bool lin_hist_pending = false;          // filled by a match, not yet consumed by a reject
   bool lin_hist_init = false;
+  bool rsf_attr_set = false;              // k_rs_fused's dynamic shared memory limit raised on this device
+  DevBuf<unsigned int> rsf_ticket;        // blocks-finished counter of the barrier-free reject/solve kernel
+  int n_fused_last = 0, n_rerun_last = 0; // last run: iterations through k_rs_fused / repeated after a missed prediction
+  int fused = 1;                          // option "fused": 0 = always the cooperative kernel
   bool bf_attr_set = false;               // k_bf_nn's dynamic shared memory limit raised on this device
   sicp_iter_record* rec_host = nullptr;  // pinned
   double* scal_host = nullptr;           // pinned staging for small reads
@@ -143,6 +149,8 @@ void estimate_normals_launch(Ctx& c, int k);
 void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve, bool arm_stop,
                          int rec_slot);
 void compact_residuals_launch(Ctx& c);
+void rs_fused_launch(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, int rec_slot, bool want_sigma);
+void final_residuals_launch(Ctx& c);
 void transform_launch(Ctx& c, const Rigid& T, const double* in_dev, double* out_dev, long long n);
 void gather_queries_launch(Ctx& c);
 

@@ -131,9 +131,31 @@ __device__ __forceinline__ double plane_distance_rec(const Rigid& T, const Rec& 
 // Feed the predictor histogram of the reject kernel (reject_solve.cuh: lh_bin): one spread-out
 // atomic per planarity survivor instead of a separate pass over the distances later.
 __device__ __forceinline__ void lin_hist_add(const DevState* st, unsigned int* lin_hist,
-                                             float planarity, double d) {
-  if (lin_hist != nullptr && st->pred_valid && (double)planarity >= st->pred_minpl)
-    atomicAdd(&lin_hist[lh_bin(d, st->pred_med, st->pred_mad)], 1u);
+                                             float planarity, double d, unsigned short* code_out) {
+  unsigned short code = LH_CODE_NONE;
+  if (lin_hist != nullptr && st->pred_valid && (double)planarity >= st->pred_minpl) {
+    const int b = lh_bin(d, st->pred_med, st->pred_mad);
+    atomicAdd(&lin_hist[b], 1u);
+    code = (unsigned short)b;
+  }
+  // the bin of every member of the statistics set, kept per correspondence: the fused
+  // reject/solve kernel finds its order-statistic candidates by scanning these 2-byte codes
+  if (code_out) *code_out = code;
+}
+
+// Epilogue data of one correspondence for the fused reject/solve kernel: the matched movable
+// point in caller coordinates (so the moment pass streams it instead of chasing nn_idx ->
+// mov_xyz) and the histogram code.
+struct CorrOut {
+  unsigned short* code;  // K, may be null
+  double* m_xyz;         // K x 3, may be null
+};
+__device__ __forceinline__ void store_matched(const CorrOut& co, long long qi, double x, double y, double z) {
+  if (co.m_xyz) {
+    co.m_xyz[3 * qi + 0] = x;
+    co.m_xyz[3 * qi + 1] = y;
+    co.m_xyz[3 * qi + 2] = z;
+  }
 }
 
 __global__ void __launch_bounds__(128)
@@ -141,7 +163,7 @@ __global__ void __launch_bounds__(128)
                  const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz, long long K,
                  int rmax, int with_distance, long long* __restrict__ nn_idx,
                  double* __restrict__ out, unsigned int* __restrict__ unresolved,
-                 unsigned int* __restrict__ lin_hist, double cap2) {
+                 unsigned int* __restrict__ lin_hist, double cap2, CorrOut co) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= K || st->stop) return;
   const Rigid Tinv = st->Tinv;
@@ -161,7 +183,8 @@ __global__ void __launch_bounds__(128)
     const float4 nr = q_nrm[i];
     const double d = plane_distance(st->T, mov_xyz, bidx, px, py, pz, nr);
     out[i] = d;
-    lin_hist_add(st, lin_hist, nr.w, d);
+    lin_hist_add(st, lin_hist, nr.w, d, co.code ? co.code + i : nullptr);
+    store_matched(co, i, mov_xyz[3 * bidx + 0], mov_xyz[3 * bidx + 1], mov_xyz[3 * bidx + 2]);
   } else {
     out[i] = best;
   }
@@ -179,7 +202,7 @@ __global__ void __launch_bounds__(128)
                       const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz,
                       long long K, int rmax, int with_distance, long long* __restrict__ nn_idx,
                       double* __restrict__ out, unsigned int* __restrict__ unresolved,
-                      unsigned int* __restrict__ lin_hist, double cap2) {
+                      unsigned int* __restrict__ lin_hist, double cap2, CorrOut co) {
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long qi = gt / MG;
   const int sub = threadIdx.x & (MG - 1);
@@ -327,9 +350,11 @@ __global__ void __launch_bounds__(128)
     const float4 nr = q_nrm[qi];
     // the winner's record was read a moment ago by a lane of this warp: same coordinates as
     // mov_xyz[bidx], but from L1/L2 instead of a cold line
-    const double d = plane_distance_rec(st->T, g.recs[bpos], px, py, pz, nr);
+    const Rec m = g.recs[bpos];
+    const double d = plane_distance_rec(st->T, m, px, py, pz, nr);
     out[qi] = d;
-    lin_hist_add(st, lin_hist, nr.w, d);
+    lin_hist_add(st, lin_hist, nr.w, d, co.code ? co.code + qi : nullptr);
+    store_matched(co, qi, m.x, m.y, m.z);
   } else {
     out[qi] = best;
   }
@@ -580,7 +605,7 @@ __global__ void __launch_bounds__(128)
                   const float4* __restrict__ q_nrm,
                   const double* __restrict__ mov_xyz, int with_distance,
                   long long* __restrict__ nn_idx, double* __restrict__ out,
-                  unsigned int* __restrict__ lin_hist) {
+                  unsigned int* __restrict__ lin_hist, CorrOut co) {
   const long long nq = qlist ? (long long)(*qcount_ptr) : q_total;
   const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (qi >= nq || st->stop) return;
@@ -600,7 +625,8 @@ __global__ void __launch_bounds__(128)
     const float4 nr = q_nrm[q];
     const double dd = plane_distance(T, mov_xyz, ix, q_xyz[3 * q + 0], q_xyz[3 * q + 1], q_xyz[3 * q + 2], nr);
     out[q] = dd;
-    lin_hist_add(st, lin_hist, nr.w, dd);
+    lin_hist_add(st, lin_hist, nr.w, dd, co.code ? co.code + q : nullptr);
+    store_matched(co, q, mov_xyz[3 * ix + 0], mov_xyz[3 * ix + 1], mov_xyz[3 * ix + 2]);
   } else {
     out[q] = d;
   }
@@ -633,6 +659,10 @@ void gather_queries_launch(Ctx& c) {
 
 // Brute-force pass over either the unresolved list (qlist != nullptr) or all K queries.
 static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
+  if (with_distance) {
+    c.corr_code.reserve(std::max<long long>(c.K, 1));
+    c.m_xyz.reserve(3 * std::max<long long>(c.K, 1));
+  }
   // the attribute belongs to the (device-specific) function handle: once per context, not per process
   if (!c.bf_attr_set) {
     SICP_CUDA(cudaFuncSetAttribute(k_bf_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBfSmem));
@@ -661,7 +691,8 @@ static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
       partials);
   k_bf_finalize<<<(unsigned)((q_total + 127) / 128), 128, 0, c.stream>>>(
       partials, n_chunks, q_total, qlist, qcount, c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p,
-      with_distance ? 1 : 0, c.nn_idx.p, out, with_distance ? c.lin_hist.p : nullptr);
+      with_distance ? 1 : 0, c.nn_idx.p, out, with_distance ? c.lin_hist.p : nullptr,
+      with_distance ? CorrOut{c.corr_code.p, c.m_xyz.p} : CorrOut{nullptr, nullptr});
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 2;
 }
@@ -679,6 +710,9 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   c.nn_idx.reserve(K);
   c.dist.reserve(K);
   c.unresolved.reserve(K + 1);
+  c.corr_code.reserve(std::max<long long>(K, 1));
+  c.m_xyz.reserve(3 * std::max<long long>(K, 1));
+  const CorrOut co = with_distance ? CorrOut{c.corr_code.p, c.m_xyz.p} : CorrOut{nullptr, nullptr};
   double* out = with_distance ? c.dist.p : out_d2;
   if (c.nn_engine == SICP_NN_BRUTE) {
     bf_launch(c, with_distance, out, true);
@@ -692,7 +726,7 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   if (c.match_group == 1) {
     k_match_grid<<<(unsigned)((K + 127) / 128), 128, 0, c.stream>>>(
         c.gmov.view(), c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p, K, rmax,
-        with_distance ? 1 : 0, c.nn_idx.p, out, c.unresolved.p, lh, cap2);
+        with_distance ? 1 : 0, c.nn_idx.p, out, c.unresolved.p, lh, cap2, co);
   } else {
     // lanes per query: 16 while the search is latency-bound (few queries), fewer once there are
     // enough queries to fill the machine and issue slots become the limit
@@ -704,7 +738,7 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   k_match_grid_coop<N><<<blocks, 128, 0, c.stream>>>(c.gmov.view(), c.dev_state.p, c.q_xyz.p, \
                                                     c.q_nrm.p, c.mov_xyz.p, K, rmax,          \
                                                     with_distance ? 1 : 0, c.nn_idx.p, out,   \
-                                                    c.unresolved.p, lh, cap2)
+                                                    c.unresolved.p, lh, cap2, co)
     if (mg == 4) SICP_LAUNCH_COOP(4);
     else if (mg == 8) SICP_LAUNCH_COOP(8);
     else SICP_LAUNCH_COOP(16);

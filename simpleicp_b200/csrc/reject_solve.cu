@@ -1294,6 +1294,581 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
   }
 }
 
+// =============================================================================================
+// k_rs_fused — the same five steps WITHOUT grid barriers and without a cooperative launch.
+//
+// The cooperative kernel above spends half its time in four grid barriers and in serial sections
+// that 147 SMs wait for (profiles/r1_phase_timeline.md).  Here every dependency is resolved by
+// construction instead of by waiting:
+//   select     every block derives median and MAD ITSELF from the predictor histogram the match
+//              kernel filled plus a scan of the 2-byte bin codes it stored per correspondence
+//              (200 KB at K = 100 000, L2 resident): redundant, identical work on every SM, no
+//              exchange.  Same exact order statistics as predicted_median_mad().
+//   accumulate each block streams its share of (normal, distance, matched point, fixed point) —
+//              the match kernel stored the matched point, so there is no index chase — and
+//              writes keep flags and per-block partial sums.
+//   solve      the block that takes the LAST ticket reduces the partials in a fixed order and runs
+//              the Gauss-Newton loop; everybody else has already left the SM.
+//   statistics mean and standard deviation of the residuals at the solution come from the moment
+//              sums themselves (sum r = theta . sum phi, sum r^2 = theta^T M theta): no residual pass
+//              and no barrier in the loop.  The residual VECTOR of the final iteration is evaluated
+//              once, after the loop (k_final_residuals), in the reference's operation order, and
+//              its statistics are recomputed two-pass from it.
+// If the prediction does not bracket the order statistics (large change between iterations) the
+// kernel changes nothing, raises state->stop = 3 and the host re-runs that iteration with the
+// general kernel (capi.cu: run_loop).
+// =============================================================================================
+constexpr int RSF_NACC = 30;             // accumulators per role
+constexpr int RSF_NPART = 3 * RSF_NACC;  // partial sums per block
+
+struct SharedF {
+  Shared s;
+  unsigned int cidx[2][RS_CAP];  // correspondences in the median bins / the MAD bracket
+  unsigned int n_cand[2];
+  double redf[RS_WARPS][RSF_NACC];
+  double totf[RSF_NPART];
+  double m1[13];  // sum phi
+  int is_last;
+};
+
+// Plan + gather + selection; true on success (median, mad, n1 set; n1 == 0 is a success).
+__device__ bool fused_select(SharedF& sf, const RSArgs& a, RSWork wk, const DevState* st,
+                             unsigned int& n1_out, double& median, double& mad) {
+  Shared& s = sf.s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int PER = (LH_BINS + RS_THREADS - 1) / RS_THREADS;
+  const int b0 = tid * PER;
+  unsigned int v[PER], sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int b = b0 + j;
+    v[j] = (b < LH_BINS) ? __ldcg(&wk.lin_hist[b]) : 0u;
+    sum += v[j];
+  }
+  unsigned int incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s.scan_tmp[warp] = incl;
+  if (tid < 2) sf.n_cand[tid] = 0;
+  __syncthreads();
+  unsigned int woff = 0, total_in = 0;
+  for (int i = 0; i < RS_WARPS; ++i) {
+    if (i < warp) woff += s.scan_tmp[i];
+    total_in += s.scan_tmp[i];
+  }
+  {
+    unsigned int run = woff + incl - sum;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      run += v[j];
+      if (b0 + j < LH_BINS) s.hist[b0 + j] = run;  // inclusive prefix sums
+    }
+  }
+  if (tid == 0) {
+    s.lh_i[0] = -1;
+    s.lh_i[1] = -1;
+    s.lh_i[2] = LH_BINS + 1;
+    s.lh_i[3] = -1;
+  }
+  __syncthreads();
+  const unsigned int* P = s.hist;
+  const unsigned int under = __ldcg(&wk.lin_hist[LH_BINS]), over = __ldcg(&wk.lin_hist[LH_BINS + 1]);
+  const unsigned int n1 = under + total_in + over;
+  n1_out = n1;
+  if (n1 == 0) return true;
+  const unsigned int k = (n1 - 1) >> 1;
+  const bool even = ((n1 & 1u) == 0u);
+  const unsigned int k2 = k + (even ? 1u : 0u);
+  if (k < under || k2 >= under + total_in) return false;
+  const unsigned int r = k - under, r2 = k2 - under;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int b = b0 + j;
+    if (b < LH_BINS) {
+      const unsigned int pb = P[b], pa = (b > 0) ? P[b - 1] : 0u;
+      if (pa <= r && r < pb) s.lh_i[0] = b;
+      if (pa <= r2 && r2 < pb) s.lh_i[1] = b;
+    }
+  }
+  __syncthreads();
+  const int bm = s.lh_i[0], bm2 = s.lh_i[1];
+  if (bm < 0 || bm2 < bm) return false;
+  const int g = bm2 - bm;
+  if (g > 4) return false;
+  const unsigned int below_m = (bm > 0) ? P[bm - 1] : 0u;
+  const unsigned int cnt_med = P[bm2] - below_m;
+  if (cnt_med > (unsigned int)(RS_CAP - 2)) return false;
+  const unsigned int kA = r - below_m;
+  auto Nin = [&](int t) -> unsigned int {
+    const int hi = min(bm2 + t, LH_BINS - 1), lo = bm - t - 1;
+    return P[hi] - ((lo >= 0) ? P[lo] : 0u);
+  };
+  int tmin = LH_BINS + 1, tmax = -1;
+  for (int t = tid; t <= LH_BINS; t += RS_THREADS) {
+    const unsigned int nin = Nin(t);
+    if (nin >= k2 + 1u) tmin = min(tmin, t);
+    if (nin <= k) tmax = max(tmax, t);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  }
+  if (lane == 0) {
+    atomicMin(&s.lh_i[2], tmin);
+    atomicMax(&s.lh_i[3], tmax);
+  }
+  __syncthreads();
+  const int t_hi = s.lh_i[2], t_lo = s.lh_i[3];
+  if (t_hi > LH_BINS) return false;
+  const int e_lo = max(t_lo - g, 0), e_hi = t_hi + g + 1;
+  if (bm - e_hi < 0 || bm2 + e_hi > LH_BINS - 1) return false;
+  const unsigned int n_inner = (t_lo - g - 1 >= 0) ? Nin(t_lo - g - 1) : 0u;
+  const unsigned int cnt_edge = Nin(e_hi) - n_inner;
+  if (cnt_edge > (unsigned int)(RS_CAP - 2) || k < n_inner || k2 - n_inner >= cnt_edge) return false;
+  const unsigned int kM = k - n_inner;
+
+  // ---- scan the 2-byte codes of all K correspondences (vector loads of 8 codes)
+  {
+    const unsigned short* __restrict__ code = a.code;
+    const long long K = a.K;
+    auto visit = [&](unsigned int c, long long i) {
+      if (c < (unsigned int)LH_BINS) {
+        const int b = (int)c;
+        const int delta = (b < bm) ? (bm - b) : ((b > bm2) ? (b - bm2) : 0);
+        if (delta == 0) {
+          const unsigned int p = atomicAdd(&sf.n_cand[0], 1u);
+          if (p < (unsigned int)RS_CAP) sf.cidx[0][p] = (unsigned int)i;
+        }
+        if (delta >= e_lo && delta <= e_hi) {
+          const unsigned int p = atomicAdd(&sf.n_cand[1], 1u);
+          if (p < (unsigned int)RS_CAP) sf.cidx[1][p] = (unsigned int)i;
+        }
+      }
+    };
+    const bool aligned = (reinterpret_cast<uintptr_t>(code) & 15) == 0;
+    const long long nvec = aligned ? (K >> 3) : 0;
+    const uint4* __restrict__ c4 = reinterpret_cast<const uint4*>(code);
+    for (long long q = tid; q < nvec; q += RS_THREADS) {
+      const uint4 w = __ldcg(c4 + q);
+      const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        visit(ww[j] & 0xffffu, q * 8 + 2 * j);
+        visit(ww[j] >> 16, q * 8 + 2 * j + 1);
+      }
+    }
+    for (long long i = nvec * 8 + tid; i < K; i += RS_THREADS) visit((unsigned int)__ldcg(code + i), i);
+  }
+  __syncthreads();
+  // the codes and the histogram come from the same match pass: anything else is a stale buffer
+  if (sf.n_cand[0] != cnt_med || sf.n_cand[1] != cnt_edge) return false;
+  unsigned long long klo, khi;
+  for (int t = tid; t < (int)cnt_med; t += RS_THREADS) s.sortbuf[t] = f64_to_key(__ldcg(a.dist + sf.cidx[0][t]));
+  __syncthreads();
+  block_select(s, s.sortbuf, (int)cnt_med, kA, 64, ~0ull, klo, khi);
+  median = even ? (a.variant ? key_to_f64(khi) : 0.5 * (key_to_f64(klo) + key_to_f64(khi))) : key_to_f64(klo);
+  __syncthreads();
+  for (int t = tid; t < (int)cnt_edge; t += RS_THREADS)
+    s.sortbuf[t] = f64_to_key(fabs(__ldcg(a.dist + sf.cidx[1][t]) - median));
+  __syncthreads();
+  block_select(s, s.sortbuf, (int)cnt_edge, kM, 64, ~0ull, klo, khi);
+  mad = even ? (a.variant ? key_to_f64(khi) : 0.5 * (key_to_f64(klo) + key_to_f64(khi))) : key_to_f64(klo);
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) {
+    wk.phase_t[26] = cnt_med;
+    wk.phase_t[27] = cnt_edge;
+  }
+  return true;
+}
+
+// theta of an affine map p -> A p + b in the centred frame: [rows of A with b'_a after each, 1],
+// b' = A c_m + b - c_f.  Lanes 0..12 return their entry.
+__device__ __forceinline__ double theta_entry(const Rigid& T, const double* cm, const double* cf, int e) {
+  if (e >= 12) return 1.0;
+  const int r = e >> 2, c = e & 3;
+  if (c < 3) return T.r[r * 3 + c];
+  return T.r[r * 3 + 0] * cm[0] + T.r[r * 3 + 1] * cm[1] + T.r[r * 3 + 2] * cm[2] + T.t[r] - cf[r];
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 1) k_rs_fused(RSArgs a, RSWork wk) {
+  extern __shared__ __align__(16) unsigned char rsf_smem[];
+  SharedF& sf = *reinterpret_cast<SharedF*>(rsf_smem);
+  Shared& s = sf.s;
+  DevState* st = a.state;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long K = a.K;
+  const int G = gridDim.x;
+  if (st->stop) return;  // a previous iteration met the stop rule (or asked for a re-run)
+  RS_STAMP(0);
+
+  // ---- select (every block, identical result)
+  unsigned int n1 = 0;
+  double median = 0.0, mad = 0.0;
+  bool ok = a.hist_expected && st->pred_valid && st->pred_minpl == a.stat_minpl && st->pred_mad > 0.0;
+  if (ok) ok = fused_select(sf, a, wk, st, n1, median, mad);
+  const double lim = a.variant ? 3.0 * (1.4826 * mad) : 3.0 * mad;
+  RS_STAMP(2);
+
+  // ---- accumulate this block's share
+  const Rigid Tin = st->T;
+  double cm[3] = {a.cm[0], a.cm[1], a.cm[2]}, cf[3];
+  rigid_apply(Tin, cm[0], cm[1], cm[2], cf[0], cf[1], cf[2]);
+  if (ok && n1 != 0) {
+    const int role = warp % 3, sub = (warp / 3) * 32 + lane;  // 128 threads per role
+    double acc[RSF_NACC];
+#pragma unroll
+    for (int j = 0; j < RSF_NACC; ++j) acc[j] = 0.0;
+    const long long chunk = (K + G - 1) / G;
+    const long long i0 = blockIdx.x * chunk, i1 = min(i0 + chunk, K);
+    const float4* __restrict__ qn = a.q_nrm;
+    const double* __restrict__ dd = a.dist;
+    const double* __restrict__ mv = a.m_xyz;
+    const double* __restrict__ qx = a.q_xyz;
+    auto accumulate = [&](const float4 nr, const double d, const double p0, const double p1,
+                          const double p2, const double f0, const double f1, const double f2) {
+      const double u0 = p0 - cm[0], u1 = p1 - cm[1], u2 = p2 - cm[2];
+      const double q0 = f0 - cf[0], q1 = f1 - cf[1], q2 = f2 - cf[2];
+      const double n0 = (double)nr.x, n1d = (double)nr.y, n2 = (double)nr.z;
+      const double sc = -(n0 * q0 + n1d * q1 + n2 * q2);
+      double na, nb, nv;
+      if (role == 0) {
+        na = n0 * n0; nb = n0 * n1d; nv = n0;
+      } else if (role == 1) {
+        na = n0 * n2; nb = n1d * n1d; nv = n1d;
+      } else {
+        na = n1d * n2; nb = n2 * n2; nv = n2;
+      }
+      const double U[10] = {u0 * u0, u0 * u1, u0 * u2, u0, u1 * u1, u1 * u2, u1, u2 * u2, u2, 1.0};
+#pragma unroll
+      for (int t = 0; t < 10; ++t) {
+        acc[t] = fma(na, U[t], acc[t]);
+        acc[10 + t] = fma(nb, U[t], acc[10 + t]);
+      }
+      const double sn = sc * nv;
+      acc[20] = fma(sn, u0, acc[20]);
+      acc[21] = fma(sn, u1, acc[21]);
+      acc[22] = fma(sn, u2, acc[22]);
+      acc[23] += sn;
+      // sum phi (for the mean of the residuals): n_role (x) (u, 1)
+      acc[26] = fma(nv, u0, acc[26]);
+      acc[27] = fma(nv, u1, acc[27]);
+      acc[28] = fma(nv, u2, acc[28]);
+      acc[29] += nv;
+      if (role == 0) {
+        acc[24] = fma(sc, sc, acc[24]);
+        acc[25] += 1.0;
+      } else if (role == 1) {
+        acc[24] += d;
+        acc[25] = fma(d, d, acc[25]);
+      } else {
+        acc[24] += sc;
+      }
+    };
+    // everything is streamed (no index chase): two elements per trip, all loads up front
+    for (long long i = i0 + sub; i < i1; i += 256) {
+      const long long ib = i + 128;
+      const bool hb = ib < i1;
+      const long long jb = hb ? ib : i;
+      const float4 nrA = qn[i], nrB = qn[jb];
+      const double dA = dd[i], dB = dd[jb];
+      const double pA0 = mv[3 * i + 0], pA1 = mv[3 * i + 1], pA2 = mv[3 * i + 2];
+      const double pB0 = mv[3 * jb + 0], pB1 = mv[3 * jb + 1], pB2 = mv[3 * jb + 2];
+      const double fA0 = qx[3 * i + 0], fA1 = qx[3 * i + 1], fA2 = qx[3 * i + 2];
+      const double fB0 = qx[3 * jb + 0], fB1 = qx[3 * jb + 1], fB2 = qx[3 * jb + 2];
+      const bool kA = ((double)nrA.w >= a.min_planarity) && (fabs(dA - median) <= lim);
+      const bool kB = hb && ((double)nrB.w >= a.min_planarity) && (fabs(dB - median) <= lim);
+      if (kA) accumulate(nrA, dA, pA0, pA1, pA2, fA0, fA1, fA2);
+      if (kB) accumulate(nrB, dB, pB0, pB1, pB2, fB0, fB1, fB2);
+      if (role == 0) {
+        a.keep[i] = kA ? 1 : 0;
+        if (hb) a.keep[ib] = kB ? 1 : 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RSF_NACC; ++j) {
+      const double vv = warp_sum(acc[j]);
+      if (lane == 0) sf.redf[warp][j] = vv;
+    }
+    __syncthreads();
+    if (tid < RSF_NPART) {
+      const int r = tid / RSF_NACC, j = tid % RSF_NACC;
+      double vv = 0.0;
+      for (int ww = r; ww < RS_WARPS; ww += 3) vv += sf.redf[ww][j];
+      wk.partials[(size_t)tid * G + blockIdx.x] = vv;
+    }
+  }
+  RS_STAMP(3);
+
+  // ---- ticket: the last block to arrive owns the serial part
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(wk.ticket, 1u);
+    sf.is_last = (t == (unsigned int)G - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!sf.is_last) return;
+  __threadfence();
+  if (tid == 0) {
+    *wk.ticket = 0u;
+    wk.phase_t[4] = global_timer_ns();
+    wk.phase_t[28] = 2;  // fused path
+  }
+  // the predictor histogram has been consumed by every block: leave it zeroed for the next match
+  for (int i = tid; i < LH_BINS + 2; i += RS_THREADS) wk.lin_hist[i] = 0;
+  sicp_iter_record* rec = a.rec;
+  if (!ok) {
+    if (tid == 0) st->stop = 3;  // re-run this iteration with the general kernel (host)
+    return;
+  }
+  if (n1 == 0) {
+    if (tid == 0) {
+      rec->n_kept = 0;
+      rec->median = rec->mad = nan("");
+      st->n_kept = 0;
+    }
+    return;
+  }
+  {
+    // fixed-order sum of the per-block partials ([value][block] layout, all loads in flight)
+    constexpr int NO = (RSF_NPART + RS_WARPS - 1) / RS_WARPS;
+    constexpr int NB = 8;  // 32 * 8 = 256 blocks max
+    double r[NO][NB];
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+      const int o = warp + q * RS_WARPS;
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int b = lane + 32 * u;
+        r[q][u] = (o < RSF_NPART && b < G) ? __ldcg(&wk.partials[(size_t)o * G + b]) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+      const int o = warp + q * RS_WARPS;
+      double vv = 0.0;
+#pragma unroll
+      for (int u = 0; u < NB; ++u) vv += r[q][u];
+      vv = warp_sum(vv);
+      if (lane == 0 && o < RSF_NPART) sf.totf[o] = vv;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) wk.phase_t[17] = global_timer_ns();
+  for (int e = tid; e < 169 + 13; e += RS_THREADS) {
+    if (e >= 169) {
+      const int o = e - 169;
+      sf.m1[o] = (o == 12) ? sf.totf[2 * RSF_NACC + 24] : sf.totf[(o / 4) * RSF_NACC + 26 + (o % 4)];
+      continue;
+    }
+    const int r = e / 13, c = e % 13;
+    double vv;
+    if (r == 12 && c == 12) {
+      vv = sf.totf[0 * RSF_NACC + 24];
+    } else if (r == 12 || c == 12) {
+      const int o = (r == 12) ? c : r;
+      vv = sf.totf[(o / 4) * RSF_NACC + 20 + (o % 4)];
+    } else {
+      int aa = r / 4, bb = r % 4, cc = c / 4, dd2 = c % 4;
+      if (aa > cc) { int t = aa; aa = cc; cc = t; }
+      if (bb > dd2) { int t = bb; bb = dd2; dd2 = t; }
+      const int i6 = (aa == 0) ? cc : (aa == 1 ? 2 + cc : 5);
+      const int i10 = (bb == 0) ? dd2 : (bb == 1 ? 3 + dd2 : (bb == 2 ? 5 + dd2 : 9));
+      vv = sf.totf[(i6 / 2) * RSF_NACC + (i6 % 2) * 10 + i10];
+    }
+    s.M[r][c] = vv;
+  }
+  __syncthreads();
+  if (tid == 0) wk.phase_t[18] = global_timer_ns();
+  if (warp != 0) return;
+
+  const long long n_kept = (long long)(sf.totf[0 * RSF_NACC + 25] + 0.5);
+  const double sum_d = sf.totf[1 * RSF_NACC + 24], sum_d2 = sf.totf[1 * RSF_NACC + 25];
+  const double mean_d = (n_kept > 0) ? sum_d / (double)n_kept : nan("");
+  const double var_d = (n_kept > 0) ? fmax(sum_d2 / (double)n_kept - mean_d * mean_d, 0.0) : nan("");
+  const double var_d1 = (n_kept > 1) ? fmax(sum_d2 - (double)n_kept * mean_d * mean_d, 0.0) / (double)(n_kept - 1) : nan("");
+  double w = st->w;
+  if (a.variant) {
+    w = 1.0;
+  } else if (a.it == 0 || !(w > 0.0)) {
+    w = a.w_param;
+    if (!(w > 0.0)) w = 1.0 / var_d;
+  }
+  const int skip = (n_kept < 6) || !a.do_solve;
+  LmOut lo;
+  lo.iters = 0;
+  lo.ok = 1;
+  if (!skip && a.variant) {
+    lin_solve(s, st->T, cf, lane);
+    lo.iters = 1;
+    lo.ok = s.spd;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) lo.x[j] = s.delta[j];
+  } else if (!skip) {
+    lm_solve(s, a, w, st->x, cm, cf, lo, lane);
+  }
+  if (lane == 0) {
+    wk.phase_t[19] = global_timer_ns();
+    wk.phase_t[21] = s.stamp[0];
+    wk.phase_t[22] = s.stamp[1];
+    rec->n_kept = n_kept;
+    rec->median = median;
+    rec->mad = mad;
+    st->pred_med = median;
+    st->pred_mad = mad;
+    st->pred_minpl = a.stat_minpl;
+    st->pred_valid = (mad > 0.0 && isfinite(mad) && isfinite(median)) ? 1 : 0;
+    rec->mean_dist = mean_d;
+    rec->std_dist = sqrt(a.variant ? var_d1 : var_d);
+    rec->distance_weight = w;
+    rec->lm_iterations = lo.iters;
+    rec->n_bruteforce = a.unresolved ? (int)a.unresolved[K] : 0;
+    st->n_kept = n_kept;
+    st->skip = skip;
+    st->w = w;
+    if (n_kept < 6 && a.do_solve && a.arm_stop) st->stop = 2;
+  }
+  if (skip) return;
+  // new transform(s)
+  Rigid T_new, T_res;
+  if (a.variant) {
+    const Rigid dH = rigid_from_x(lo.x);
+    T_new = rigid_compose(dH, Tin);
+    Rigid L;
+    L.r[0] = 1.0; L.r[1] = -lo.x[2]; L.r[2] = lo.x[1];
+    L.r[3] = lo.x[2]; L.r[4] = 1.0; L.r[5] = -lo.x[0];
+    L.r[6] = -lo.x[1]; L.r[7] = lo.x[0]; L.r[8] = 1.0;
+    L.t[0] = lo.x[3]; L.t[1] = lo.x[4]; L.t[2] = lo.x[5];
+    T_res = rigid_compose(L, Tin);
+  } else {
+    T_new = rigid_from_x(lo.x);
+    T_res = T_new;
+  }
+  // residual statistics at the solution from the moments: r_i = phi_i . theta
+  const double th = theta_entry(T_res, cm, cf, min(lane, 12));
+  double rowdot = 0.0, s1 = 0.0;
+  if (lane < 13) {
+#pragma unroll
+    for (int m = 0; m < 13; ++m) rowdot = fma(s.M[lane][m], __shfl_sync(0x1fffu, th, m), rowdot);
+    rowdot *= th;
+    s1 = sf.m1[lane] * th;
+  }
+  const double sum_r2 = fmax(warp_sum(rowdot), 0.0);
+  const double sum_r = warp_sum(s1);
+  const double n = (double)n_kept;
+  const double mean = sum_r / n;
+  const double sd = a.variant ? sqrt(fmax(sum_r2 - n * mean * mean, 0.0) / (n - 1.0))
+                              : sqrt(fmax(sum_r2 / n - mean * mean, 0.0));
+  int stop = 0;
+  if (a.it > 0) {
+    const double m0 = st->prev_mean, s0 = st->prev_std;
+    const double cmn = (m0 == 0.0) ? ((mean == 0.0) ? 0.0 : kInf) : fabs((mean - m0) / m0 * 100.0);
+    const double csd = (s0 == 0.0) ? ((sd == 0.0) ? 0.0 : kInf) : fabs((sd - s0) / s0 * 100.0);
+    stop = (cmn < a.min_change && csd < a.min_change) ? 1 : 0;
+  }
+  if (a.variant) {
+    if (lane < 6) {
+      st->sigma[lane] = nan("");
+      rec->x[lane] = lo.x[lane];
+    }
+  } else {
+    if ((stop && a.arm_stop) || a.want_sigma) {
+      if (lane < 36) st->An[lane] = s.Ak[lane];
+      if (lane + 32 < 36) st->An[lane + 32] = s.Ak[lane + 32];
+      __syncwarp();
+      uncertainties(s, a, s.Ak, w, lo.x, sum_r2, n_kept, lane, st->sigma);
+    }
+    if (lane < 6) {
+      rec->x[lane] = lo.x[lane];
+      st->x[lane] = lo.x[lane];
+      st->x_new[lane] = lo.x[lane];
+    }
+  }
+  if (lane == 0) {
+    if (a.variant) {
+      for (int j = 0; j < 6; ++j) st->x_new[j] = lo.x[j];
+      const Rigid dH = rigid_from_x(lo.x);
+      const Rigid Hr = st->H_rep;
+      st->H_rep = (a.variant == SICP_VARIANT_LINEARIZED_CPP) ? rigid_compose(Hr, dH) : rigid_compose(dH, Hr);
+    } else {
+      st->H_rep = T_new;
+    }
+    st->lm_ok = lo.ok;
+    st->T_new = T_new;
+    st->T_res = T_res;
+    st->T = T_new;
+    st->Tinv = rigid_inverse(T_new);
+    rec->mean_res = mean;
+    rec->std_res = sd;
+    st->prev_mean = mean;
+    st->prev_std = sd;
+    st->iterations_done = a.it + 1;
+    if (stop && a.arm_stop) st->stop = 1;
+    st->converged = stop;
+    wk.phase_t[9] = global_timer_ns();
+  }
+}
+
+// Residual vector of the LAST iteration (reference operation order, optimization.py:117-124) for
+// the kept correspondences, from the matched points the match kernel stored.  One launch after
+// the loop; the compaction and the exact two-pass statistics follow (k_resid_stats).
+__global__ void __launch_bounds__(256)
+    k_final_residuals(const DevState* __restrict__ st, const uint8_t* __restrict__ keep,
+                      const double* __restrict__ m_xyz, const double* __restrict__ q_xyz,
+                      const float4* __restrict__ q_nrm, long long K, double* __restrict__ resid) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= K || !keep[i]) return;
+  const Rigid Tn = st->T_res;
+  double tx, ty, tz;
+  rigid_apply(Tn, m_xyz[3 * i + 0], m_xyz[3 * i + 1], m_xyz[3 * i + 2], tx, ty, tz);
+  const float4 nr = q_nrm[i];
+  const double dx = tx - q_xyz[3 * i + 0], dy = ty - q_xyz[3 * i + 1], dz = tz - q_xyz[3 * i + 2];
+  resid[i] = __dadd_rn(__dadd_rn(__dmul_rn(dx, (double)nr.x), __dmul_rn(dy, (double)nr.y)),
+                       __dmul_rn(dz, (double)nr.z));
+}
+
+// Exact statistics of the compacted residuals: mean first, then the squared deviations from it
+// (two passes, one block, fixed order) — written over the moment-based values of the last record.
+__global__ void __launch_bounds__(1024)
+    k_resid_stats(const double* __restrict__ r, const DevState* __restrict__ st, int sample_std,
+                  sicp_iter_record* __restrict__ rec_base) {
+  __shared__ double sh[32];
+  __shared__ double mean_s;
+  const long long n = st->n_kept;
+  const int it = st->iterations_done - 1;
+  if (n <= 0 || it < 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) acc += r[i];
+  acc = warp_sum(acc);
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += sh[i];
+    mean_s = t / (double)n;
+  }
+  __syncthreads();
+  const double mean = mean_s;
+  acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const double d = r[i] - mean;
+    acc = fma(d, d, acc);
+  }
+  acc = warp_sum(acc);
+  __syncthreads();
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += sh[i];
+    rec_base[it].mean_res = mean;
+    rec_base[it].std_res = sample_std ? sqrt(t / (double)(n - 1)) : sqrt(t / (double)n);
+  }
+}
+
 // Ordered compaction of the kept residuals (final iteration only): block-level scan, one block
 // per 4096 elements, two kernels.
 __global__ void __launch_bounds__(256)
@@ -1437,6 +2012,79 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
     k_reject_solve<false><<<1, RS_THREADS, 0, c.stream>>>(a, wk);
     SICP_CUDA(cudaGetLastError());
   }
+  c.tm.kernel_launches += 1;
+}
+
+// Launch of the barrier-free kernel (iterations whose predecessor left a valid predictor).
+void rs_fused_launch(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, int rec_slot,
+                     bool want_sigma) {
+  const long long K = c.K;
+  const int G = (int)std::min<long long>(c.num_sms, std::max<long long>(1, (K + 767) / 768));
+  if (!c.rsf_attr_set) {
+    SICP_CUDA(cudaFuncSetAttribute(k_rs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(SharedF)));
+    c.rsf_attr_set = true;
+  }
+  c.ws.partials.reserve((size_t)c.num_sms * (RSF_NPART + 2) + 16);
+  c.keep.reserve(K);
+  c.resid.reserve(K);
+  c.phase_t.reserve(32);
+  if (c.rsf_ticket.p == nullptr) {
+    c.rsf_ticket.reserve(4);
+    SICP_CUDA(cudaMemsetAsync(c.rsf_ticket.p, 0, 4 * sizeof(unsigned int), c.stream));
+  }
+  RSArgs a;
+  a.K = K;
+  a.dist = c.dist.p;
+  a.q_nrm = c.q_nrm.p;
+  a.q_xyz = c.q_xyz.p;
+  a.nn_idx = c.nn_idx.p;
+  a.mov_xyz = c.mov_xyz.p;
+  a.keep = c.keep.p;
+  a.resid = c.resid.p;
+  a.unresolved = (c.nn_engine == SICP_NN_AUTO) ? c.unresolved.p : nullptr;
+  a.state = c.dev_state.p;
+  a.rec = c.ws.rec.p + rec_slot;
+  a.min_planarity = p.min_planarity;
+  a.variant = c.variant;
+  a.stat_minpl = c.variant ? -kInf : p.min_planarity;
+  a.min_change = p.min_change;
+  a.w_param = p.lsq.distance_weight;
+  for (int j = 0; j < 6; ++j) {
+    a.obs[j] = p.lsq.observed[j];
+    a.wobs[j] = p.lsq.obs_weight[j];
+  }
+  for (int j = 0; j < 3; ++j) a.cm[j] = c.mov_center[j];
+  a.it = it;
+  a.do_solve = 1;
+  a.arm_stop = arm_stop ? 1 : 0;
+  a.hist_expected = c.lin_hist_pending ? 1 : 0;
+  c.lin_hist_pending = false;  // the kernel leaves the histogram zeroed
+  a.code = c.corr_code.p;
+  a.m_xyz = c.m_xyz.p;
+  a.want_sigma = want_sigma ? 1 : 0;
+  RSWork wk{};
+  wk.partials = c.ws.partials.p;
+  wk.phase_t = c.phase_t.p;
+  wk.lin_hist = c.lin_hist.p;
+  wk.ticket = c.rsf_ticket.p;
+  k_rs_fused<<<G, RS_THREADS, sizeof(SharedF), c.stream>>>(a, wk);
+  SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
+}
+
+// Residual vector, ordered compaction and exact statistics of the final iteration.
+void final_residuals_launch(Ctx& c) {
+  const long long K = c.K;
+  c.resid.reserve(K);
+  k_final_residuals<<<(unsigned)((K + 255) / 256), 256, 0, c.stream>>>(
+      c.dev_state.p, c.keep.p, c.m_xyz.p, c.q_xyz.p, c.q_nrm.p, K, c.resid.p);
+  SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
+  compact_residuals_launch(c);
+  k_resid_stats<<<1, 1024, 0, c.stream>>>(c.resid_compact.p, c.dev_state.p, c.variant != SICP_VARIANT_PYTHON,
+                                         c.ws.rec.p);
+  SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 1;
 }
 
