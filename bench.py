@@ -16,11 +16,16 @@ value      = K * steps / (sum of the per-step device times); every step starts w
              (a 256 MiB buffer is overwritten between steps, outside the timed intervals),
              inputs resident in HBM.  Per-step times are CUDA-event intervals on the launching
              stream; with N ranks the slowest rank's total is used.
-e2e        = the same metric through the public API call  simpleicp(X_fix, X_mov,
-             correspondences=K)  on pinned HOST arrays: upload, grid builds, normals, the
-             whole iteration loop, final transform and download are all inside the timed region.
-N > 1      = independent pairs, one per GPU (weak scaling); the only collective is the NCCL
-             all-gather of the per-pair result records, inside the e2e region.
+e2e        = the same metric through the public API call  simpleicp_b200.register(X_fix, X_mov,
+             correspondences=K)  (what simpleicp() runs) on pinned HOST arrays: upload, grid
+             builds, normals, the whole iteration loop, final transform and download are all
+             inside the timed region.  Beside it: the same call on pageable arrays with the
+             library's default engine (e2e_simpleicp_pageable) and the drop-in class
+             SimpleICP().run() on pandas point clouds (e2e_class_run).
+N > 1      = independent pairs, one per GPU (weak scaling); the only collective is ONE NCCL
+             all-gather of the per-pair result records after the last registration.
+c4 / c5    = BASELINE configs[3] and [4] measured through their public entry points
+             (tile_slabs + register per slab; simpleicp_batch), spread over the N ranks.
 """
 from __future__ import annotations
 
@@ -42,14 +47,32 @@ METRIC = "correspondences/sec per ICP iter (1M<->1M pts)"
 UNIT = "corr/s"
 
 
+def workload_string(n: int, K: int) -> str:
+    """Identical in both arms (the driver compares the strings)."""
+    return (f"C3 synthetic surface pair {n}<->{n} per GPU, correspondences={K}, neighbors=10, "
+            "min_planarity=0.3 (BASELINE.json configs[2])")
+
+
 def make_pair(n: int, rank: int):
     """C3 generator; rank r uses seeds shifted by 10 r (independent pairs)."""
-    from oracle.simpleicp_oracle import rbp_to_H, surface, transform_by_H  # input generator only
+    from simpleicp_b200 import synthetic
 
-    H_true = rbp_to_H([np.deg2rad(0.3), np.deg2rad(-0.2), np.deg2rad(0.5), 0.15, -0.10, 0.05])
-    X_fix = surface(n, 1234 + 10 * rank)
-    X_mov = transform_by_H(surface(n, 5678 + 10 * rank), np.linalg.inv(H_true))
-    return np.ascontiguousarray(X_fix), np.ascontiguousarray(X_mov), H_true
+    return synthetic.c3_pair(n, shift=10 * rank)
+
+
+def make_c5_pairs(ids, n_pts: int = 100_000, pinned: bool = False, total: int = 512):
+    """Pairs `ids` of the C5 batch as host arrays (optionally pinned)."""
+    from simpleicp_b200 import synthetic
+
+    out = []
+    for i in ids:
+        Xf, Xm, _ = synthetic.c5_pair(i, n_pts, total)
+        if pinned:
+            import torch
+
+            Xf, Xm = torch.from_numpy(Xf).pin_memory().numpy(), torch.from_numpy(Xm).pin_memory().numpy()
+        out.append((Xf, Xm))
+    return out
 
 
 def algorithmic_bytes(n_mov: int, K: int, n_kept: int):
@@ -69,7 +92,6 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.samples = []
-        self.marks = []
         self.proc = None
         try:
             self.proc = subprocess.Popen(
@@ -100,52 +122,176 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sel)}
 
 
-def run_reference(args):
-    """CPU arm: the oracle port of the reference's algorithm (NumPy + SciPy cKDTree + TRF), the
-    same SciPy calls the reference makes, on this host's cores.  One step = one ICP iteration."""
+# ------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------
+def _reference_worker(args_tuple):
+    """One reference process: the oracle port on ITS pair with its share of the host cores."""
+    n, K, warmup, steps, pair_id, workers = args_tuple
     from oracle import simpleicp_oracle as O
 
+    O.WORKERS = workers
+    X_fix, X_mov, _ = _oracle_pair(O, n, pair_id)
+    tr = O.Trace(light=True)
+    n_it = warmup + steps
+    t0 = time.perf_counter()
+    O.simpleicp(X_fix, X_mov, correspondences=K, min_change=0.0, max_iterations=n_it, trace=tr)
+    total = time.perf_counter() - t0
+    return tr.iter_seconds, total, tr.timings.get("normals")
+
+
+def _oracle_pair(O, n, pair_id):
+    H_true = O.rbp_to_H([np.deg2rad(0.3), np.deg2rad(-0.2), np.deg2rad(0.5), 0.15, -0.10, 0.05])
+    X_fix = O.surface(n, 1234 + 10 * pair_id)
+    X_mov = O.transform_by_H(O.surface(n, 5678 + 10 * pair_id), np.linalg.inv(H_true))
+    return X_fix, X_mov, H_true
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's algorithm (NumPy + SciPy cKDTree + TRF), the
+    same SciPy calls the reference makes, on this host's cores.  One step = one ICP iteration.
+    With --gpus N it registers N independent pairs side by side (N processes, the cores split
+    between them) — the like-for-like counterpart of the N-GPU weak-scaling run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    X_fix, X_mov, _ = make_pair(args.points, 0)
-    tr = O.Trace(light=True)
-    n_it = args.warmup + args.steps
+    cores = os.cpu_count() or 1
+    n_proc = max(1, int(args.gpus))
+    workers = max(1, cores // n_proc)
+    jobs = [(args.points, args.correspondences, args.warmup, args.steps, r, workers if n_proc > 1 else -1)
+            for r in range(n_proc)]
     t0 = time.perf_counter()
-    O.simpleicp(X_fix, X_mov, correspondences=args.correspondences, min_change=0.0,
-                max_iterations=n_it, trace=tr)
-    total = time.perf_counter() - t0
-    it_s = tr.iter_seconds[args.warmup:]
-    loop = float(np.sum(it_s))
-    value = args.correspondences * len(it_s) / loop
-    e2e = args.correspondences * n_it / total
-    cores = os.cpu_count()
-    sample = (f"{n_it} ICP iterations (first {args.warmup} untimed) of the oracle port on the full C3 pair, "
-              f"K={args.correspondences}; cKDTree queries use all {cores} cores (workers=-1), tree build, "
-              "transforms, eig loop and TRF solve are single-threaded as in the reference")
+    if n_proc == 1:
+        results = [_reference_worker(jobs[0])]
+    else:
+        import multiprocessing as mp
+
+        with mp.get_context("spawn").Pool(n_proc) as pool:
+            results = pool.map(_reference_worker, jobs)
+    wall = time.perf_counter() - t0
+    n_it = args.warmup + args.steps
+    loops = [float(np.sum(it_s[args.warmup:])) for it_s, _, _ in results]
+    totals = [tot for _, tot, _ in results]
+    steps = len(results[0][0][args.warmup:])
+    value = n_proc * args.correspondences * steps / max(loops)
+    e2e = n_proc * args.correspondences * n_it / max(totals)
+    sample = (f"{n_it} ICP iterations (first {args.warmup} untimed) of the oracle port on "
+              f"{n_proc} full C3 pair(s) side by side ({n_proc} process(es), {workers if n_proc > 1 else cores} cKDTree "
+              f"worker threads each), K={args.correspondences}; tree build, transforms, eig loop and TRF solve are "
+              "single-threaded as in the reference")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(it_s), "warmup": args.warmup, "ms_per_step": 1e3 * loop / len(it_s),
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * max(loops) / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"C3 synthetic surface pair {args.points}<->{args.points}, correspondences={args.correspondences}, neighbors=10",
-                   "l2": "n/a (CPU)"},
+        "config": {"workload": workload_string(args.points, args.correspondences), "l2": "n/a (CPU)",
+                   "pairs_side_by_side": n_proc},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "setup_s": {"normals": tr.timings.get("normals"), "total": total},
+        "setup_s": {"normals": results[0][2], "total": max(totals), "wall": wall},
     }))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local: int):
+    """Pinned buffers are first-touched by this process: run it on the GPU's own NUMA node."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out  # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = []
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001 — best effort, containers often hide the topology
+        return None
+
+
+def run_c4(sb, eng, rank, world, local):
+    """BASELINE configs[3]: the airborne pair cut into 8 overlapping slabs along x (25 m overlap,
+    SURVEY.md §8d C4), one registration per slab, slabs dealt round-robin to the ranks."""
+    import torch
+
+    fixture = REPO / "tests" / "golden" / "data_airborne.npz"
+    if not fixture.exists():
+        return None
+    sys.path.insert(0, str(REPO / "tests"))
+    from conftest import load_golden, load_pair
+
+    X_fix, X_mov = load_pair("airborne")
+    H_ref = load_golden("airborne")["H"]
+    slabs = sb.tile_slabs(X_fix, X_mov, 8, overlap=25.0)
+    mine = list(range(rank, 8, world))
+    pinned = [(torch.from_numpy(slabs[s][0]).pin_memory().numpy(), torch.from_numpy(slabs[s][1]).pin_memory().numpy())
+              for s in mine]
+    out = []
+    for (Xf, Xm) in pinned[:1]:
+        sb.register(Xf, Xm, engine=eng, want_normals=False)  # warm-up (buffer growth)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s, (Xf, Xm) in zip(mine, pinned):
+        t1 = time.perf_counter()
+        r = sb.register(Xf, Xm, engine=eng, want_normals=False)
+        out.append({"slab": s, "n_fix": int(Xf.shape[0]), "n_mov": int(Xm.shape[0]), "iterations": r.iterations,
+                    "ms": 1e3 * (time.perf_counter() - t1), "H_frobenius_vs_whole_cloud_reference": float(np.linalg.norm(r.H - H_ref))})
+    torch.cuda.synchronize()
+    return {"slabs": out, "seconds": time.perf_counter() - t0}
+
+
+def run_c5(sb, rank, world, local, dist, pairs_per_gpu, n_pts):
+    """BASELINE configs[4]: 64 x N independent 100k-point pairs (512 on 8 GPUs), through
+    simpleicp_batch (batched engine: one launch set per stage and iteration for a rank's share,
+    NCCL all-gather of the records)."""
+    import torch
+
+    n_pairs = pairs_per_gpu * world
+    mine = list(range(rank, n_pairs, world))
+    local_pairs = dict(zip(mine, make_c5_pairs(mine, n_pts, pinned=True, total=max(512, n_pairs))))
+    get = lambda i: local_pairs[i]  # noqa: E731 — only this rank's share is ever asked for
+    kw = dict(rank=rank, world_size=world, dist=dist if world > 1 else None, device=local, on_error="nan",
+              batch_size=pairs_per_gpu)
+    sb.simpleicp_batch(get, n_pairs, **kw)  # warm-up (buffer growth)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    table = sb.simpleicp_batch(get, n_pairs, **kw)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    from simpleicp_b200 import synthetic
+
+    x_true = synthetic.c5_transforms(max(512, n_pairs))
+    errs = [float(np.linalg.norm(table[i, :16].reshape(4, 4) - synthetic.H_from_rbp(x_true[i]))) for i in range(n_pairs)
+            if table[i, 16] > 0]
+    return {"pairs": n_pairs, "points_per_cloud": n_pts, "seconds": dt, "pairs_per_s": n_pairs / dt,
+            "failed": int((table[:, 16] < 0).sum()), "mean_iterations": float(table[table[:, 16] > 0, 16].mean()),
+            "max_H_frobenius_vs_H_true": max(errs) if errs else None,
+            "api": "simpleicp_b200.simpleicp_batch(pairs, engine='batched') on pinned host arrays, records all-gathered"}
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    import simpleicp_b200 as sb
-    from simpleicp_b200 import _capi, batch
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+
+    import simpleicp_b200 as sb
+    from simpleicp_b200 import _capi, batch
+
     torch.cuda.set_device(local)
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner off it
@@ -166,7 +312,7 @@ def run_b200(args):
     eng.set_clouds(Xf_pin.numpy(), Xm_pin.numpy())
     idx = sb.pointcloud.subsample_indices(n, K).astype(np.int64)
     eng.set_selected(idx)
-    nrm = eng.estimate_normals(10)
+    eng.estimate_normals(10)
     lsq = eng.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
     params = eng.run_params(0.3, 1.0, 100, lsq)
 
@@ -176,16 +322,18 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- warm-up then the timed region (cold L2 before every step)
+    # ---- warm-up: a real registration's worth of iterations brings the loop to its steady state
+    # (the state every iteration after the first few of a registration is in), then the timed
+    # region (cold L2 before every step)
     rec = eng.iterate(params, x_in=np.zeros(6), want_record=True)
-    for _ in range(max(args.warmup - 1, 0)):
+    for _ in range(max(args.warmup - 1, 11)):
         rec = eng.iterate(params, want_record=True)
     launches0 = eng.timings()["kernel_launches"]
     barrier()
-    t_region0 = time.time()
     st = eng.time_stages(params, args.steps, True)
     barrier()
     launches = eng.timings()["kernel_launches"] - launches0
+    path = eng.phase_times()[28]
     total_ms = st["iteration"] * args.steps
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -196,9 +344,6 @@ def run_b200(args):
     n_kept = int(rec.n_kept)
 
     # ---- same loop, warm L2, iterations queued back to back with no host sync (what sicp_run does)
-    eng.iterate(params, x_in=np.zeros(6))
-    for _ in range(args.warmup):
-        eng.iterate(params)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -220,44 +365,75 @@ def run_b200(args):
 
     # ---- end to end through the public API on pinned host arrays
     def one_e2e():
-        res = sb.register(Xf_pin.numpy(), Xm_pin.numpy(), correspondences=K, engine=eng,
-                          transform_out=out_pin.numpy(), want_normals=False)  # = what simpleicp() does
-        tab = None
-        if world > 1:
-            last = res.records[res.iterations - 1]
-            local_rec = batch.pack_record(res.H, res.iterations, last["n_kept"], last["mean_res"], last["std_res"])[None]
-            tab = batch.gather_records(local_rec, world, world, rank, dist, torch.device("cuda", local))
-        return res, tab
+        return sb.register(Xf_pin.numpy(), Xm_pin.numpy(), correspondences=K, engine=eng,
+                           transform_out=out_pin.numpy(), want_normals=False)  # = what simpleicp() does
 
     one_e2e()  # warm-up (allocations)
     barrier()
     t0 = time.perf_counter()
     its = 0
     for _ in range(args.e2e_steps):
-        res, tab = one_e2e()
+        res = one_e2e()
         its += res.iterations
-    barrier()
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    tm = eng.timings()
+    # the one collective of the multi-GPU run: the result records, gathered once after the last
+    # registration (inside the reported time)
     if world > 1:
+        last = res.records[res.iterations - 1]
+        local_rec = batch.pack_record(res.H, res.iterations, last["n_kept"], last["mean_res"], last["std_res"])[None]
+        tg = time.perf_counter()
+        batch.gather_records(local_rec, world, world, rank, dist, torch.device("cuda", local))
+        e2e_s += time.perf_counter() - tg
         t = torch.tensor([e2e_s, float(its)], dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        e2e_s, its_total = float(tmax[0].item()), float(tsum[1].item())
+        e2e_s_max, its_total = float(tmax[0].item()), float(tsum[1].item())
     else:
-        its_total = float(its)
-    e2e_value = K * its_total / e2e_s
+        e2e_s_max, its_total = e2e_s, float(its)
+    e2e_value = K * its_total / e2e_s_max
     dH_true = float(np.linalg.norm(res.H - H_true))
-    tm = eng.timings()
 
-    # ---- the linearised variant on the same pair: same two kernels
-    # per iteration, one linear solve instead of the Gauss-Newton loop; reported beside the headline
+    # ---- the north-star API as a user calls it: pageable arrays, no engine argument; and the class
+    extra = {}
+    if world == 1:
+        H1, X1, rbp1, r1 = sb.simpleicp(X_fix, X_mov, correspondences=K)  # warm-up: default engine creation
+        t0 = time.perf_counter()
+        for _ in range(3):
+            H1, X1, rbp1, r1 = sb.simpleicp(X_fix, X_mov, correspondences=K)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        extra["e2e_simpleicp_pageable"] = {
+            "ms_per_registration": 1e3 * dt, "value": K * res.iterations / dt, "unit": UNIT,
+            "api": "simpleicp_b200.simpleicp(X_fix, X_mov, correspondences=K) on pageable NumPy arrays, library-owned engine"}
+        pc_fix = sb.PointCloud(X_fix, columns=["x", "y", "z"])
+        icp = sb.SimpleICP(verbose=False)
+        t_cls = []
+        for _ in range(2):
+            pc_fix.select_all_points()
+            for col in ("nx", "ny", "nz", "planarity"):
+                if col in pc_fix:
+                    del pc_fix[col]
+            pc_mov = sb.PointCloud(X_mov, columns=["x", "y", "z"], copy=True)
+            icp.add_point_clouds(pc_fix, pc_mov)
+            t0 = time.perf_counter()
+            Hc, Xc, rbpc, rc = icp.run(correspondences=K)
+            t_cls.append(time.perf_counter() - t0)
+        extra["e2e_class_run"] = {
+            "ms_per_registration": 1e3 * min(t_cls), "value": K * res.iterations / min(t_cls), "unit": UNIT,
+            "H_equals_functional_api": bool(np.array_equal(Hc, H1)),
+            "api": "SimpleICP().add_point_clouds(PointCloud, PointCloud); .run(correspondences=K) — pandas containers, "
+                   "normals stored back as columns, pc_mov transformed in place"}
+
+    # ---- the linearised variant on the same pair
     variants = None
     if world == 1:
         eng.set_option("variant", 1)
         eng.iterate(params, x_in=np.zeros(6), want_record=True)
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(args.warmup, 11)):
             eng.iterate(params, want_record=True)
         st_lin = eng.time_stages(params, args.steps, True)
         t0 = time.perf_counter()
@@ -271,6 +447,23 @@ def run_b200(args):
             "kernels_ms_cold_l2": st_lin, "e2e_ms_per_registration": 1e3 * lin_s, "e2e_iterations": rl.iterations,
             "H_frobenius_vs_H_true": float(np.linalg.norm(rl.T - H_true)),
             "api": "simpleicp_b200.simpleicp_linearized(X_fix, X_mov, correspondences=K, engine=<reused>)"}}
+
+    # ---- BASELINE configs[3] and [4] through their public entry points (all ranks take part)
+    c4 = c5 = None
+    if not args.no_c4c5:
+        try:
+            c4 = run_c4(sb, eng, rank, world, local)
+            if c4 is not None and world > 1:
+                gathered = [None] * world
+                dist.all_gather_object(gathered, c4)
+                c4 = {"slabs": sorted(sum((g["slabs"] for g in gathered), []), key=lambda s: s["slab"]),
+                      "seconds": max(g["seconds"] for g in gathered)}
+            if c4 is not None:
+                c4["config"] = "airborne_lidar1/2 (1 342 906 points each) cut into 8 slabs along x, 25 m overlap, defaults"
+                c4["slabs_per_s"] = 8 / c4["seconds"]
+            c5 = run_c5(sb, rank, world, local, dist, args.c5_pairs_per_gpu, args.c5_points)
+        except Exception as e:  # noqa: BLE001 — the headline line must not depend on the side configs
+            c5 = c5 or {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -289,10 +482,11 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    rs_name = {2.0: "k_rs_fused", 1.0: "k_reject_solve", 0.0: "k_reject_solve"}.get(path, "k_reject_solve")
     if st["match_grid"] >= st["reject_solve"]:
         dom, dom_ms, dom_bytes = "k_match_grid_coop", st["match_grid"], b_match
     else:
-        dom, dom_ms, dom_bytes = "k_reject_solve", st["reject_solve"], b_rs
+        dom, dom_ms, dom_bytes = rs_name, st["reject_solve"], b_rs
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9
     traffic = None
     prof = REPO / "profiles" / "ncu_traffic.json"
@@ -305,6 +499,11 @@ def run_b200(args):
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                 "kernels_ms_cold_l2": st, "kernels_ms_warm_l2": st_warm,
+                "reject_solve_kernel": rs_name,
+                "per_kernel": {"k_match_grid_coop": {"algorithmic_bytes": b_match, "ms": st["match_grid"],
+                                                     "frac": b_match / (st["match_grid"] * 1e-3) / 1e9 / peak},
+                               rs_name: {"algorithmic_bytes": b_rs, "ms": st["reject_solve"],
+                                         "frac": b_rs / (st["reject_solve"] * 1e-3) / 1e9 / peak}},
                 "iteration_bytes": b_match + b_rs,
                 "note": "the search structure is L2-resident in the real loop; see DESIGN.md for the L2/latency view"}
 
@@ -338,21 +537,24 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3 synthetic surface pair {n}<->{n} per GPU, correspondences={K}, neighbors=10, "
-                               "min_planarity=0.3 (BASELINE.json configs[2])",
+        "config": {"workload": workload_string(n, K),
                    "l2": "flushed: 256 MiB buffer overwritten before every timed step",
-                   "nn_engine": "grid (float64) + TMA brute-force fallback", "kept_per_iteration": n_kept},
+                   "nn_engine": "grid (float64, warm-started from the previous iteration's match) + TMA brute-force fallback",
+                   "kept_per_iteration": n_kept, "numa_node_bound": numa},
         "value_l2_warm_queued": world * K / (warm_ms * 1e-3),
         "ms_per_step_l2_warm_queued": warm_ms,
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 24,
                 "d2h_bytes_per_step": n * 24 + 8 * n_kept,
-                "ms_per_registration": 1e3 * e2e_s / args.e2e_steps, "iterations": its_total / (args.e2e_steps * world),
+                "ms_per_registration": 1e3 * e2e_s_max / args.e2e_steps, "iterations": its_total / (args.e2e_steps * world),
                 "registrations": args.e2e_steps,
                 "api": "simpleicp_b200.register(X_fix, X_mov, correspondences=K, engine=<reused>, transform_out=<pinned>)",
                 "stage_ms": {k: v for k, v in tm.items() if k.endswith("_ms")},
-                "H_frobenius_vs_H_true": dH_true},
+                "iterations_in_barrier_free_kernel": tm.get("fused_iterations"),
+                "iterations_repeated_in_general_kernel": tm.get("rerun_iterations"),
+                "H_frobenius_vs_H_true": dH_true, **extra},
         "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "variants": variants,
+        "c4": c4, "c5": c5,
     }
     print(json.dumps(line))
     if world > 1:
@@ -369,6 +571,9 @@ def main():
     ap.add_argument("--correspondences", type=int, default=100_000)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4c5", action="store_true")
+    ap.add_argument("--c5-pairs-per-gpu", type=int, default=64)
+    ap.add_argument("--c5-points", type=int, default=100_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "b200" else 0)
     if args.impl == "reference":

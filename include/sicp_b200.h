@@ -220,6 +220,32 @@ int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz /*[h|d] n_fix x 3*/, 
                       double* mov_xyz_out /*[h|d] n_mov x 3 or NULL*/,
                       int64_t* n_selected /*[h] or NULL*/);
 
+/* ---- many independent pairs in one call (BASELINE.json configs[4]) --------
+ * SimpleICP.run (simpleicp.py:75-324, defaults: no overlap filter) for n_pairs independent
+ * (fixed, movable) pairs on ONE GPU with ONE set of kernel launches per stage and per iteration
+ * for the whole batch: the grids of all 2 n_pairs clouds are built in one segmented counting
+ * sort, the searches of all pairs run in one launch, reject + solve run one block per pair, every
+ * pair has its own stop flag.  Results per pair equal those of sicp_register on that pair.
+ * fix_xyz[i] / mov_xyz[i] point to the i-th pair's clouds (host, ideally pinned, or device);
+ * correspondences must be <= 4096 (one block per pair) and max_overlap_distance must be unused.
+ * out[i].status is the sicp_status of pair i (a pair without enough correspondences fails alone);
+ * the call itself fails only on bad arguments or CUDA errors.                                   */
+typedef struct {
+  int32_t status;
+  int32_t iterations;
+  int32_t converged;
+  int32_t reserved;
+  int64_t n_kept;
+  double H[16];
+  double x[6];
+  double sigma[6];
+  double mean_res, std_res;   /* of the final residuals (exact, two-pass)                       */
+} sicp_pair_result;
+int32_t sicp_register_batch(sicp_ctx* ctx, int32_t n_pairs, const double* const* fix_xyz /*[h|d]*/,
+                            const int64_t* n_fix, const double* const* mov_xyz /*[h|d]*/,
+                            const int64_t* n_mov, const sicp_register_params* p,
+                            sicp_pair_result* out /*[h] n_pairs*/);
+
 /* ---- PointCloud.transform_by_H (pointcloud.py:205-217), final application simpleicp.py:316 -- */
 int32_t sicp_transform(sicp_ctx* ctx, const double H[16], double* mov_xyz_out /*[h|d] n_mov x 3*/);
 

@@ -31,6 +31,10 @@ from scipy.optimize import least_squares
 
 PARAM_NAMES = ("alpha1", "alpha2", "alpha3", "tx", "ty", "tz")
 
+# threads of the cKDTree queries (the reference passes workers=-1: all cores).  bench.py lowers it
+# when it runs several reference processes side by side (one per GPU of the arm it is compared with).
+WORKERS = -1
+
 
 # --------------------------------------------------------------------------- mathutils.py
 def euler_angles_to_rotation_matrix(a1: float, a2: float, a3: float) -> np.ndarray:
@@ -77,7 +81,7 @@ def select_in_range(
     than max_range (cKDTree distance_upper_bound semantics)."""
     kdtree = spatial.cKDTree(X_other)
     distances, _ = kdtree.query(
-        X_fix[idx_sel], k=1, p=2, distance_upper_bound=max_range, workers=-1
+        X_fix[idx_sel], k=1, p=2, distance_upper_bound=max_range, workers=WORKERS
     )
     return idx_sel[np.isfinite(distances)]
 
@@ -98,7 +102,7 @@ def estimate_normals(
     normal = eigenvector of the smallest eigenvalue, planarity = (l_mid - l_min) / l_max,
     both stored as float32.  Returns (normals f32 [K,3], planarity f32 [K], idxNN [K,k])."""
     kdtree = spatial.cKDTree(X_fix)
-    _, idxNN_all = kdtree.query(X_fix[idx_sel], k=neighbors, p=2, workers=-1)
+    _, idxNN_all = kdtree.query(X_fix[idx_sel], k=neighbors, p=2, workers=WORKERS)
     if idxNN_all.ndim == 1:
         idxNN_all = idxNN_all[:, None]
     normals = np.full((idx_sel.size, 3), np.nan, dtype=np.float32)
@@ -125,7 +129,7 @@ def match(
     selected fixed point, signed point-to-plane distance (dx*nx + dy*ny) + dz*nz with the
     float32 normal promoted to float64."""
     kdtree = spatial.cKDTree(X_mov_transformed)
-    _, idx_nn = kdtree.query(X_fix[idx_sel], k=1, p=2, workers=-1)
+    _, idx_nn = kdtree.query(X_fix[idx_sel], k=1, p=2, workers=WORKERS)
     p1 = X_fix[idx_sel]
     p2 = X_mov_transformed[idx_nn]
     n = normals_f32.astype(np.float64)
@@ -374,7 +378,7 @@ def simpleicp(
         t_it = time.perf_counter()
         if static_tree:
             q = transform_by_H(X_fix[idx_sel], np.linalg.inv(H))
-            _, idx_nn = tree_static.query(q, k=1, p=2, workers=-1)
+            _, idx_nn = tree_static.query(q, k=1, p=2, workers=WORKERS)
             p2t = transform_by_H(X2[idx_nn], H)
             p1 = X_fix[idx_sel]
             n64 = nrm.astype(np.float64)

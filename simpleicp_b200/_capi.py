@@ -28,7 +28,7 @@ SYMBOLS = (
     "sicp_set_normals", "sicp_get_knn", "sicp_match", "sicp_reject", "sicp_solve",
     "sicp_uncertainties", "sicp_run", "sicp_get_transform", "sicp_get_residuals", "sicp_iterate", "sicp_transform",
     "sicp_select_n_points", "sicp_register",
-    "sicp_get_timings", "sicp_time_stages", "sicp_get_phase_times",
+    "sicp_register_batch", "sicp_get_timings", "sicp_time_stages", "sicp_get_phase_times",
     "sicp_xyz_load", "sicp_xyz_free", "sicp_xyz_save", "sicp_io_last_error",
 )
 
@@ -67,6 +67,13 @@ class Timings(C.Structure):
                                           "transform_ms")] + [("kernel_launches", C.c_int64),
                                                             ("fused_iterations", C.c_int64),
                                                             ("rerun_iterations", C.c_int64)]
+
+
+class PairResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("converged", C.c_int32),
+                ("reserved", C.c_int32), ("n_kept", C.c_int64), ("H", C.c_double * 16),
+                ("x", C.c_double * 6), ("sigma", C.c_double * 6), ("mean_res", C.c_double),
+                ("std_res", C.c_double)]
 
 
 class SicpError(RuntimeError):
@@ -137,6 +144,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "sicp_select_n_points": [vp, i64, vp],
         "sicp_register": [vp, vp, i64, vp, i64, C.POINTER(RegisterParams), C.POINTER(RunResult),
                           C.POINTER(IterRecord), vp, C.POINTER(i64)],
+        "sicp_register_batch": [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64),
+                                C.POINTER(RegisterParams), C.POINTER(PairResult)],
         "sicp_get_timings": [vp, C.POINTER(Timings)],
         "sicp_time_stages": [vp, C.POINTER(RunParams), i32, i32, C.POINTER(dbl)],
         "sicp_get_phase_times": [vp, C.POINTER(dbl)],
@@ -434,6 +443,26 @@ class Engine:
         res = np.empty(int(out.n_residuals), dtype=np.float64)
         self._check(self._lib.sicp_get_residuals(self._h, _ptr(res), res.size, C.byref(n)))
         return out, [log[i] for i in range(out.iterations)], res, transform_out
+
+    def register_batch(self, pairs, correspondences, neighbors, params: RunParams):
+        """sicp_register_batch: SimpleICP.run for every (X_fix, X_mov) of `pairs` with one set of
+        kernel launches per stage for the whole batch.  Clouds are NumPy arrays (pinned ones
+        upload at link speed) or CUDA tensors; nothing is copied on the host.  Returns the
+        ctypes array of PairResult (status per pair)."""
+        n = len(pairs)
+        keep = [(_as_f64_xyz(a), _as_f64_xyz(b)) for a, b in pairs]  # keeps converted copies alive
+        fp = (C.c_void_p * n)(*[_ptr(a) for a, _ in keep])
+        mp = (C.c_void_p * n)(*[_ptr(b) for _, b in keep])
+        nf = (C.c_int64 * n)(*[int(a.shape[0]) for a, _ in keep])
+        nm = (C.c_int64 * n)(*[int(b.shape[0]) for _, b in keep])
+        rp = RegisterParams()
+        rp.correspondences = int(correspondences)
+        rp.neighbors = int(neighbors)
+        rp.max_overlap_distance = -1.0
+        rp.run = params
+        out = (PairResult * n)()
+        self._check(self._lib.sicp_register_batch(self._h, n, fp, nf, mp, nm, C.byref(rp), out))
+        return out
 
     def get_transform(self) -> np.ndarray:
         """The 4 x 4 transform the last run/solve applied to the movable cloud."""

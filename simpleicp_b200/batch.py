@@ -94,6 +94,9 @@ def close_engine_pool() -> None:
         for _, eng in pool:
             eng.close()
     _ENGINES.clear()
+    for eng in _BATCH_ENGINES.values():
+        eng.close()
+    _BATCH_ENGINES.clear()
 
 
 def simpleicp_batch(
@@ -107,6 +110,8 @@ def simpleicp_batch(
     register_fn=None,
     concurrency: int = 4,
     on_error: str = "raise",
+    batch_size: int = 64,
+    engine: str = "batched",
     **run_kwargs,
 ) -> np.ndarray:
     """Register every pair; returns the (n_pairs, 20) record table on every rank.
@@ -117,6 +122,12 @@ def simpleicp_batch(
     the collective on CPU.  On the GPU path `concurrency` engines, each on its own CUDA stream and
     driven by its own thread (the C calls release the GIL), work through the rank's share so the
     host round trips of small registrations overlap.
+
+    `engine="batched"` (default) hands the rank's share to the library's batched engine in chunks
+    of `batch_size` pairs (sicp_register_batch: one set of kernel launches per stage and per
+    iteration for the whole chunk, a block per pair for reject + solve, per-pair stop flags);
+    pairs it does not cover (overlap filter, more than 4096 correspondences, debug output) and
+    `engine="pool"` use the concurrent per-pair engines described above.
 
     A pair that cannot be registered (no overlap, fewer than 6 correspondences: ordinary
     data-dependent outcomes) gets a NaN record whose `iterations` field is minus the library's
@@ -150,6 +161,8 @@ def simpleicp_batch(
         for j, i in enumerate(mine):
             Xf, Xm = get(i)
             local[j] = guarded(register_fn, Xf, Xm, **run_kwargs)
+    elif engine == "batched" and _batchable(run_kwargs):
+        _run_batched(get, mine, local, device, batch_size, run_kwargs, messages)
     else:
         import threading
 
@@ -196,6 +209,54 @@ def simpleicp_batch(
     if failed.size and on_error == "raise":
         raise BatchError(table, failed, messages)
     return table
+
+
+_BATCH_KEYS = {"correspondences", "neighbors", "min_planarity", "min_change", "max_iterations",
+               "distance_weights", "rbp_observed_values", "rbp_observation_weights", "max_overlap_distance",
+               "want_normals"}
+
+
+def _batchable(kw) -> bool:
+    """Can the batched engine serve these run() arguments?  (One block per pair: at most 4096
+    correspondences; no overlap filter; nothing that needs per-pair host interaction.)"""
+    if set(kw) - _BATCH_KEYS:
+        return False
+    if np.isfinite(kw.get("max_overlap_distance", np.inf)):
+        return False
+    return int(kw.get("correspondences", 1000)) <= 4096 and not kw.get("want_normals", False)
+
+
+_BATCH_ENGINES: dict = {}
+
+
+def _run_batched(get, mine, local, device, batch_size, kw, messages):
+    import torch
+
+    from . import _capi
+    from .simpleicp import _check_arguments, _observed_in_radians
+
+    dw = kw.get("distance_weights", 1)
+    obs_v = kw.get("rbp_observed_values", (0.0,) * 6)
+    obs_w = kw.get("rbp_observation_weights", (0.0,) * 6)
+    _check_arguments(dw, obs_v, obs_w)
+    obs = _observed_in_radians(obs_v)
+    with torch.cuda.device(device):
+        eng = _BATCH_ENGINES.get(int(device))
+        if eng is None or not eng.alive:
+            eng = _BATCH_ENGINES[int(device)] = _capi.Engine(int(device))
+        lsq = eng.lsq_params(obs, obs, [float(w) for w in obs_w], dw)
+        params = eng.run_params(kw.get("min_planarity", 0.3), kw.get("min_change", 1.0),
+                                kw.get("max_iterations", 100), lsq)
+        for lo in range(0, len(mine), max(1, int(batch_size))):
+            ids = range(lo, min(lo + max(1, int(batch_size)), len(mine)))
+            pairs = [get(mine[j]) for j in ids]
+            res = eng.register_batch(pairs, kw.get("correspondences", 1000), kw.get("neighbors", 10), params)
+            for j, r in zip(ids, res):
+                if r.status == 0:
+                    local[j] = pack_record(np.array(r.H).reshape(4, 4), r.iterations, r.n_kept, r.mean_res, r.std_res)
+                else:
+                    messages.append(f"pair {mine[j]}: library status {r.status}")
+                    local[j] = pack_record(np.full((4, 4), np.nan), -int(r.status), 0, np.nan, np.nan)
 
 
 class BatchError(RuntimeError):

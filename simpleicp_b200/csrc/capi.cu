@@ -8,11 +8,6 @@
 
 #include "ctx.cuh"
 
-struct sicp_ctx {
-  sicp::Ctx c;
-  int it_counter = 0;
-};
-
 namespace sicp {
 
 static thread_local std::string g_thread_error;
@@ -133,7 +128,9 @@ void launch_iteration(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, i
                       bool allow_fused, bool want_sigma, cudaEvent_t mid = nullptr, cudaEvent_t after_match = nullptr) {
   match_launch(c, true, nullptr, mid, c.expect_unresolved);
   if (after_match) SICP_CUDA(cudaEventRecord(after_match, c.stream));
-  if (allow_fused && c.fused && it > 0)
+  // K <= 4096: one block owns the whole problem and falls back to the radix selection by itself
+  // when there is no prediction (first iteration) — the barrier-free kernel serves every iteration
+  if (allow_fused && c.fused && (it > 0 || c.K <= 4096))
     rs_fused_launch(c, p, it, arm_stop, rec_slot, want_sigma);
   else
     reject_solve_launch(c, p, it, true, arm_stop, rec_slot);
@@ -258,6 +255,8 @@ int32_t sicp_destroy(sicp_ctx* ctx) {
   if (c.ev_copy) cudaEventDestroy(c.ev_copy);
   if (c.ev_user) cudaEventDestroy(c.ev_user);
   if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+  delete c.batch;
+  c.batch = nullptr;
   if (c.rec_host) cudaFreeHost(c.rec_host);
   if (c.scal_host) cudaFreeHost(c.scal_host);
   delete ctx;
@@ -280,6 +279,7 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.match_group = d.match_group;
     c.host_sync_every = d.host_sync_every;
     c.fused = d.fused;
+    c.warm_start = d.warm_start;
   } else if (k == "nn_engine") {
     SICP_REQUIRE(value == 0 || value == 1 || value == 2, SICP_ERR_BAD_ARG, "nn_engine must be 0, 1 or 2");
     c.nn_engine = (int)value;
@@ -297,6 +297,8 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.grid_max_rings = (int)value;
   } else if (k == "grid_sort_cells") {
     c.grid_sort_cells = (value != 0) ? 1 : 0;
+  } else if (k == "warm_start") {
+    c.warm_start = (value != 0) ? 1 : 0;
   } else if (k == "fused") {
     c.fused = (value != 0) ? 1 : 0;
   } else if (k == "rs_blocks") {
@@ -337,6 +339,7 @@ int32_t sicp_set_selected(sicp_ctx* ctx, const int64_t* idx, int64_t K) {
   c.K = K;
   gather_queries_launch(c);
   c.have_normals = false;
+  c.nn_pos_valid = false;
   c.matched = c.rejected = c.solved = false;
   sync(c);
   API_END
@@ -376,6 +379,7 @@ int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, con
   SICP_CUDA(cudaStreamSynchronize(c.copy_stream));  // the caller may reuse fix_xyz after return
   c.K = 0;
   c.have_normals = false;
+  c.nn_pos_valid = false;
   c.matched = c.rejected = c.solved = false;
   API_END
 }
@@ -630,7 +634,8 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
   SICP_CUDA(cudaEventCreate(&e0));
   SICP_CUDA(cudaEventCreate(&e1));
   SICP_CUDA(cudaEventRecord(e0, c.stream));
-  int done = 0, fetched = 0, converged = 0, n_fused = 0, n_rerun = 0;
+  int done = 0, fetched = 0, converged = 0, n_rerun = 0;
+  std::vector<char> path((size_t)p->max_iterations, 0);  // 1: iteration served by the barrier-free kernel
   DevState h;
   // host reads: after each of the first two iterations (they decide whether the brute-force
   // pass is still needed), then every host_sync_every iterations; the device-side stop flag turns
@@ -640,9 +645,9 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
   int general_at = -1;  // iteration to repeat with the general kernel (fused prediction missed)
   c.expect_unresolved = true;
   for (int it = 0; it < p->max_iterations; ++it) {
-    const bool fused = c.fused && it > 0 && it != general_at;
+    const bool fused = c.fused && (it > 0 || c.K <= 4096) && it != general_at;
     launch_iteration(c, *p, it, true, it, fused, it + 1 == p->max_iterations);
-    n_fused += fused ? 1 : 0;
+    path[(size_t)it] = fused ? 1 : 0;
     tr(fused ? "it (fused)" : "it (general)", it);
     if (it >= next_sync || it + 1 == p->max_iterations) {
       next_sync = (it < 2) ? it + 1 : it + every;
@@ -656,7 +661,6 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
         // queued behind it returned immediately.  Repeat from there with the general kernel.
         clear_stop_flag(c);
         SICP_CUDA(cudaMemsetAsync(c.ws.rec.p + done, 0, sizeof(sicp_iter_record) * (size_t)(it + 1 - done), c.stream));
-        n_fused -= (it + 1 - done);
         general_at = done;
         fetched = std::min(fetched, done);
         it = done - 1;
@@ -689,7 +693,8 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
   SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
   if (h.iterations_done > 0 || done > 0) fetch_records(c, std::max(done - 1, 0), 1);
   sync(c);
-  c.n_fused_last = n_fused;
+  c.n_fused_last = 0;
+  for (int i = 0; i < h.iterations_done && i < p->max_iterations; ++i) c.n_fused_last += path[(size_t)i];
   c.n_rerun_last = n_rerun;
   tr("final", -1);
   float ms = 0;
@@ -781,6 +786,7 @@ int32_t sicp_select_n_points(sicp_ctx* ctx, int64_t n, int64_t* idx_out) {
     c.K = n;
     gather_queries_launch(c);
     c.have_normals = false;
+    c.nn_pos_valid = false;
     c.matched = c.rejected = c.solved = false;
   }
   if (idx_out) copy_any(c, idx_out, c.sel_idx.p, sizeof(long long) * c.K);
@@ -812,6 +818,7 @@ int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, const
   c.gfix.built = false;
   c.K = 0;
   c.have_normals = false;
+  c.nn_pos_valid = false;
   c.matched = c.rejected = c.solved = false;
   // Transfers in the order the pipeline consumes them.  The fixed cloud goes first on the
   // context's stream; the movable cloud follows on the copy stream, and while it crosses PCIe the

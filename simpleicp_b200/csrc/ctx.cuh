@@ -47,6 +47,8 @@ struct SolveWs {
   DevBuf<sicp_iter_record> rec;     // device copy of the per-iteration record ring
 };
 
+struct Batch;
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -87,8 +89,13 @@ struct Ctx {
   DevBuf<long long> nn_idx;
   DevBuf<double> dist;
   DevBuf<uint8_t> keep;
-  DevBuf<unsigned short> corr_code;  // K: predictor-histogram bin of every correspondence (match -> fused reject/solve)
+  DevBuf<unsigned int> binstore;     // LH_BINS x bin_cap: members of every predictor-histogram bin (match -> fused reject/solve)
+  int bin_cap = 0;
   DevBuf<double> m_xyz;              // K x 3: matched movable point, caller coordinates
+  DevBuf<uint32_t> nn_pos;           // K: record position of the last match (warm start of the next one)
+  bool nn_pos_valid = false;         // nn_pos belongs to the current movable grid and selection
+  long long nn_pos_K = 0;
+  int warm_start = 1;                // option "warm_start"
   DevBuf<double> resid;          // K, valid where keep
   DevBuf<double> resid_compact;  // kept order
   DevBuf<unsigned int> unresolved;  // query ids the grid could not bound + counter at [K]
@@ -116,6 +123,7 @@ struct Ctx {
   DevBuf<unsigned int> lin_hist;          // predictor histogram (match kernels -> reject kernel)
   bool lin_hist_pending = false;          // filled by a match, not yet consumed by a reject
   bool lin_hist_init = false;
+  bool rsb_attr_set = false;
   bool rsf_attr_set = false;              // k_rs_fused's dynamic shared memory limit raised on this device
   DevBuf<unsigned int> rsf_ticket;        // blocks-finished counter of the barrier-free reject/solve kernel
   int n_fused_last = 0, n_rerun_last = 0; // last run: iterations through k_rs_fused / repeated after a missed prediction
@@ -130,6 +138,74 @@ struct Ctx {
 
   // staging for host inputs
   DevBuf<unsigned char> stage;
+
+  Batch* batch = nullptr;  // created by the first sicp_register_batch
+};
+
+// ---- batched engine: many small pairs per launch (BASELINE configs[4]) ----
+// One descriptor per pair, resident in device memory; every batched kernel takes the pair from
+// blockIdx.y (or blockIdx.x for the one-block-per-pair kernels) and reads its descriptor.
+struct PairDev {
+  GridView gmov, gfix;
+  long long n_fix, n_mov;
+  long long fix_off, mov_off;  // first point of this pair in the concatenated clouds
+  long long K;                 // selected fixed points (<= Kmax)
+  long long q_off;             // first entry of this pair in the per-query arrays
+  double cm[3];                // centre of the movable grid's box (moment centring)
+};
+
+// One cloud of a batched grid build (filled by the host from the bounding boxes).
+struct CloudPlan {
+  const double* xyz;
+  long long n;
+  long long rec_base;   // position of its first record in the shared record array (= point offset)
+  long long cell_base;  // first entry of its cell table in the shared table
+  double ox, oy, oz, h, inv_h;
+  int nx, ny, nz, pad;
+};
+
+// The grids of one side (all fixed or all movable clouds of a batch): one record array, one cell table.
+struct BatchGrid {
+  DevBuf<Rec> recs;
+  DevBuf<uint32_t> cell_table, fill, cid, block_sums;
+};
+
+struct Batch {
+  int n_pairs = 0;
+  long long Kmax = 0, total_fix = 0, total_mov = 0;
+  DevBuf<double> fix_xyz, mov_xyz;  // concatenated clouds
+  BatchGrid gfix, gmov;
+  DevBuf<unsigned int> occ;
+  DevBuf<unsigned long long> bbox_keys;
+  DevBuf<CloudPlan> plans;
+  DevBuf<PairDev> pairs;
+  // per-query arrays, n_pairs x Kmax
+  DevBuf<long long> sel_idx, nn_idx;
+  DevBuf<double> q_xyz, dist, m_xyz;
+  DevBuf<float4> q_nrm;
+  DevBuf<unsigned int> binstore;  // n_pairs x LH_BINS x bin_cap
+  int bin_cap = 0;
+  DevBuf<uint32_t> nn_pos;
+  DevBuf<uint8_t> keep;
+  // per-pair state
+  DevBuf<DevState> state;
+  DevBuf<unsigned int> lin_hist;       // n_pairs x (LH_BINS + 2)
+  DevBuf<sicp_iter_record> rec;        // n_pairs x max_iterations
+  DevBuf<double> partials;             // n_pairs x RSF_NPART (+ slack)
+  DevBuf<unsigned int> ticket;         // n_pairs
+  DevBuf<unsigned long long> phase_t;  // 32 (diagnostics of pair 0)
+  DevBuf<int> flags;                   // n_pairs x 2: {stop, iterations_done}
+  DevBuf<sicp_pair_result> results;
+  int* flags_host = nullptr;                 // pinned
+  sicp_pair_result* results_host = nullptr;  // pinned
+  size_t flags_cap = 0, results_cap = 0;
+  unsigned long long* keys_host = nullptr;   // pinned: bounding boxes / occupancies
+  size_t keys_cap = 0;
+  ~Batch() {
+    if (flags_host) cudaFreeHost(flags_host);
+    if (results_host) cudaFreeHost(results_host);
+    if (keys_host) cudaFreeHost(keys_host);
+  }
 };
 
 // ---- stage entry points (each implemented in its own translation unit) ---------------------
@@ -154,6 +230,22 @@ void final_residuals_launch(Ctx& c);
 void transform_launch(Ctx& c, const Rigid& T, const double* in_dev, double* out_dev, long long n);
 void gather_queries_launch(Ctx& c);
 
+// batched launches
+struct BatchHostCloud {
+  const double* xyz_dev;
+  long long n;
+  long long point_off;  // first record of this cloud in the shared record array
+};
+void grid_build_batch(Ctx& c, Batch& b, BatchGrid& bg, const std::vector<BatchHostCloud>& clouds,
+                      std::vector<GridView>& views, std::vector<double>& centres /* 3 per cloud */);
+void batch_select_gather_launch(Ctx& c, Batch& b, long long correspondences, int round_away);
+void batch_normals_launch(Ctx& c, Batch& b, int k);
+void batch_match_launch(Ctx& c, Batch& b, bool warm);
+void batch_rs_launch(Ctx& c, Batch& b, const sicp_run_params& p, int it, bool want_sigma);
+void batch_finish_launch(Ctx& c, Batch& b, int max_iterations);
+
+int bin_cap_for(long long K);
+
 // helpers in capi.cu
 bool is_device_ptr(const void* p);
 
@@ -171,3 +263,8 @@ struct StageTimer {
 };
 
 }  // namespace sicp
+
+struct sicp_ctx {
+  sicp::Ctx c;
+  int it_counter = 0;
+};

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "ctx.cuh"
 
@@ -360,6 +361,248 @@ void grid_build(Ctx& c, Grid& g, const double* xyz, long long n) {
   tr("scatter queued");
   c.tm.kernel_launches += 5;  // bbox x3, scatter, sort_cells
   g.built = true;
+}
+
+// =============================================================================================
+// Batched build: the grids of many (small) clouds in one segmented counting sort.
+//   * all clouds share one record array (cloud c owns [rec_base, rec_base + n)) and one cell table
+//     (cloud c owns [cell_base, cell_base + n_cells]); cell-table entries are GLOBAL record
+//     positions, so one exclusive scan over the concatenated counters serves every cloud and the
+//     end sentinel of a cloud is the first entry of the next;
+//   * blockIdx.y selects the cloud in every per-point kernel;
+//   * cell sizes follow the same rule as the single build (2-D manifold estimate, then refinement
+//     from the measured occupancy); the host sees bounding boxes and occupancies of the whole
+//     batch at once (three small read-backs per BATCH instead of three per cloud).
+// Rec::idx is the index inside its own cloud.
+// =============================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256) k_bbox_batch(const CloudPlan* __restrict__ plans,
+                                                    unsigned long long* __restrict__ keys) {
+  const CloudPlan pl = plans[blockIdx.y];
+  const double* __restrict__ xyz = pl.xyz;
+  double mn[3] = {kInf, kInf, kInf}, mx[3] = {-kInf, -kInf, -kInf};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pl.n;
+       i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v = xyz[3 * i + a];
+      mn[a] = fmin(mn[a], v);
+      mx[a] = fmax(mx[a], v);
+    }
+  }
+  __shared__ double smn[8][3], smx[8][3];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = warp_min(mn[a]);
+    mx[a] = warp_max(mx[a]);
+    if (lane == 0) {
+      smn[w][a] = mn[a];
+      smx[w][a] = mx[a];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    double lo = smn[0][a], hi = smx[0][a];
+    for (int i = 1; i < 8; ++i) {
+      lo = fmin(lo, smn[i][a]);
+      hi = fmax(hi, smx[i][a]);
+    }
+    atomicMin(&keys[6 * blockIdx.y + a], f64_to_key(lo));
+    atomicMax(&keys[6 * blockIdx.y + 3 + a], f64_to_key(hi));
+  }
+}
+
+__global__ void k_bbox_batch_init(unsigned long long* keys, int n_clouds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * n_clouds) keys[i] = ((i % 6) < 3) ? ~0ull : 0ull;
+}
+
+__global__ void __launch_bounds__(256) k_cell_count_batch(const CloudPlan* __restrict__ plans,
+                                                          uint32_t* __restrict__ cid,
+                                                          uint32_t* __restrict__ count,
+                                                          unsigned int* __restrict__ occ) {
+  const CloudPlan pl = plans[blockIdx.y];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= pl.n) return;
+  const int cx = cell_coord(pl.xyz[3 * i + 0], pl.ox, pl.inv_h, pl.nx);
+  const int cy = cell_coord(pl.xyz[3 * i + 1], pl.oy, pl.inv_h, pl.ny);
+  const int cz = cell_coord(pl.xyz[3 * i + 2], pl.oz, pl.inv_h, pl.nz);
+  const uint32_t cell = (uint32_t)(((long long)cz * pl.ny + cy) * pl.nx + cx);
+  cid[pl.rec_base + i] = cell;
+  if (atomicAdd(&count[pl.cell_base + cell], 1u) == 0u) atomicAdd(&occ[blockIdx.y], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_scatter_batch(const CloudPlan* __restrict__ plans,
+                                                       const uint32_t* __restrict__ cid,
+                                                       const uint32_t* __restrict__ cell_start,
+                                                       uint32_t* __restrict__ fill,
+                                                       Rec* __restrict__ recs) {
+  const CloudPlan pl = plans[blockIdx.y];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= pl.n) return;
+  const uint32_t cell = cid[pl.rec_base + i];
+  const uint32_t pos = cell_start[pl.cell_base + cell] + atomicAdd(&fill[pl.cell_base + cell], 1u);
+  Rec r;
+  r.x = pl.xyz[3 * i + 0];
+  r.y = pl.xyz[3 * i + 1];
+  r.z = pl.xyz[3 * i + 2];
+  r.idx = i;
+  recs[pos] = r;
+}
+
+inline double host_key_to_f64(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  double v;
+  std::memcpy(&v, &b, sizeof(v));
+  return v;
+}
+
+}  // namespace
+
+void grid_build_batch(Ctx& c, Batch& b, BatchGrid& bg, const std::vector<BatchHostCloud>& clouds,
+                      std::vector<GridView>& views, std::vector<double>& centres) {
+  cudaStream_t st = c.stream;
+  const int nc = (int)clouds.size();
+  long long total_pts = 0, max_n = 0;
+  for (const auto& cl : clouds) {
+    total_pts = std::max(total_pts, cl.point_off + cl.n);
+    max_n = std::max(max_n, cl.n);
+  }
+  SICP_REQUIRE(total_pts < (1ll << 32), SICP_ERR_BAD_ARG, "a batch is limited to 2^32 - 1 points in total");
+  const size_t need_keys = (size_t)nc * 8;
+  if (b.keys_cap < need_keys) {
+    if (b.keys_host) cudaFreeHost(b.keys_host);
+    SICP_CUDA(cudaMallocHost(&b.keys_host, need_keys * sizeof(unsigned long long)));
+    b.keys_cap = need_keys;
+  }
+  b.bbox_keys.reserve((size_t)nc * 6);
+  b.plans.reserve(nc);
+  b.occ.reserve(nc);
+  bg.cid.reserve(total_pts);
+  bg.recs.reserve(total_pts);
+  std::vector<CloudPlan> plans((size_t)nc);
+  for (int i = 0; i < nc; ++i) {
+    plans[(size_t)i] = CloudPlan{};
+    plans[(size_t)i].xyz = clouds[(size_t)i].xyz_dev;
+    plans[(size_t)i].n = clouds[(size_t)i].n;
+    plans[(size_t)i].rec_base = clouds[(size_t)i].point_off;
+  }
+  auto upload_plans = [&]() {
+    // pageable source: the runtime stages it before returning, `plans` may change afterwards
+    SICP_CUDA(cudaMemcpyAsync(b.plans.p, plans.data(), sizeof(CloudPlan) * (size_t)nc, cudaMemcpyHostToDevice, st));
+  };
+  upload_plans();
+  const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((max_n + 255) / 256, 64));
+  k_bbox_batch_init<<<(6 * nc + 255) / 256, 256, 0, st>>>(b.bbox_keys.p, nc);
+  k_bbox_batch<<<dim3(bx, nc), 256, 0, st>>>(b.plans.p, b.bbox_keys.p);
+  SICP_CUDA(cudaMemcpyAsync(b.keys_host, b.bbox_keys.p, sizeof(unsigned long long) * 6 * (size_t)nc,
+                            cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaStreamSynchronize(st));
+  c.tm.kernel_launches += 2;
+
+  std::vector<double> lo((size_t)nc * 3), ext((size_t)nc * 3), h((size_t)nc);
+  for (int i = 0; i < nc; ++i) {
+    double e[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[(size_t)i * 3 + a] = host_key_to_f64(b.keys_host[6 * i + a]);
+      ext[(size_t)i * 3 + a] = host_key_to_f64(b.keys_host[6 * i + 3 + a]) - lo[(size_t)i * 3 + a];
+      SICP_REQUIRE(std::isfinite(lo[(size_t)i * 3 + a]) && std::isfinite(ext[(size_t)i * 3 + a]), SICP_ERR_BAD_ARG,
+                   "point cloud contains non-finite coordinates");
+      e[a] = ext[(size_t)i * 3 + a];
+    }
+    std::sort(e, e + 3);
+    const double emax = std::max(e[2], 1e-12);
+    const double area = std::max(e[2] * std::max(e[1], 1e-3 * emax), 1e-300);
+    h[(size_t)i] = std::max(sqrt(c.grid_target_occ * area / (double)std::max<long long>(plans[(size_t)i].n, 1)), emax * 1e-6);
+  }
+  // per-cloud cell cap: generous for scans (a 2-D manifold in a 3-D box), bounded for the batch
+  auto cap_of = [&](long long n) { return std::min<long long>(1ll << 25, std::max<long long>(4096, 32 * n)); };
+  long long total_cells = 0;
+  std::vector<char> final_h((size_t)nc, 0);
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    total_cells = 0;
+    for (int i = 0; i < nc; ++i) {
+      CloudPlan& pl = plans[(size_t)i];
+      long long d[3];
+      for (;;) {
+        for (int a = 0; a < 3; ++a) d[a] = std::max<long long>(1, (long long)floor(ext[(size_t)i * 3 + a] / h[(size_t)i]) + 1);
+        if (d[0] * d[1] * d[2] <= cap_of(pl.n)) break;
+        h[(size_t)i] *= 1.26;
+        final_h[(size_t)i] = 1;  // the cap binds: no further refinement
+      }
+      pl.ox = lo[(size_t)i * 3 + 0];
+      pl.oy = lo[(size_t)i * 3 + 1];
+      pl.oz = lo[(size_t)i * 3 + 2];
+      pl.h = h[(size_t)i];
+      pl.inv_h = 1.0 / h[(size_t)i];
+      pl.nx = (int)d[0];
+      pl.ny = (int)d[1];
+      pl.nz = (int)d[2];
+      pl.cell_base = total_cells;
+      total_cells += d[0] * d[1] * d[2];
+    }
+    SICP_REQUIRE(total_cells < (1ll << 31), SICP_ERR_BAD_ARG, "batch needs too many grid cells: use smaller batches");
+    upload_plans();
+    bg.cell_table.reserve(total_cells + 1);
+    bg.fill.reserve(total_cells + 1);
+    SICP_CUDA(cudaMemsetAsync(bg.fill.p, 0, (size_t)total_cells * sizeof(uint32_t), st));
+    SICP_CUDA(cudaMemsetAsync(b.occ.p, 0, (size_t)nc * sizeof(unsigned int), st));
+    k_cell_count_batch<<<dim3((unsigned)((max_n + 255) / 256), nc), 256, 0, st>>>(b.plans.p, bg.cid.p, bg.fill.p, b.occ.p);
+    c.tm.kernel_launches += 1;
+    unsigned int* occ_host = reinterpret_cast<unsigned int*>(b.keys_host);
+    SICP_CUDA(cudaMemcpyAsync(occ_host, b.occ.p, sizeof(unsigned int) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    bool again = false;
+    for (int i = 0; i < nc && attempt < 3; ++i) {
+      if (final_h[(size_t)i]) continue;
+      const double occ = (double)plans[(size_t)i].n / (double)std::max<unsigned int>(occ_host[i], 1u);
+      if (occ <= c.grid_target_occ * 1.6 && occ >= c.grid_target_occ / 1.6) {
+        final_h[(size_t)i] = 1;
+        continue;
+      }
+      double f = pow(c.grid_target_occ / occ, 1.0 / 2.3);
+      f = std::min(std::max(f, 0.25), 4.0);
+      h[(size_t)i] *= f;
+      again = true;
+    }
+    if (!again) break;
+  }
+  // exclusive scan of the concatenated counters -> global record positions
+  const long long nsb = (total_cells + kScanItems - 1) / kScanItems;
+  bg.block_sums.reserve(nsb + 1);
+  c.misc_counters.reserve(64);
+  k_scan_reduce<<<(unsigned)nsb, 256, 0, st>>>(bg.fill.p, total_cells, bg.block_sums.p, c.misc_counters.p + 16);
+  k_scan_blocksums<<<1, 1024, 0, st>>>(bg.block_sums.p, (int)nsb);
+  k_scan_down<<<(unsigned)nsb, 256, 0, st>>>(bg.fill.p, total_cells, bg.block_sums.p, bg.cell_table.p);
+  k_scan_total<<<1, 32, 0, st>>>(bg.fill.p, total_cells, bg.cell_table.p);
+  SICP_CUDA(cudaMemsetAsync(bg.fill.p, 0, (size_t)total_cells * sizeof(uint32_t), st));
+  k_scatter_batch<<<dim3((unsigned)((max_n + 255) / 256), nc), 256, 0, st>>>(b.plans.p, bg.cid.p, bg.cell_table.p, bg.fill.p, bg.recs.p);
+  SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 5;
+  views.resize((size_t)nc);
+  centres.resize((size_t)nc * 3);
+  for (int i = 0; i < nc; ++i) {
+    const CloudPlan& pl = plans[(size_t)i];
+    GridView v;
+    v.recs = bg.recs.p;
+    v.cell_start = bg.cell_table.p + pl.cell_base;
+    v.ox = pl.ox;
+    v.oy = pl.oy;
+    v.oz = pl.oz;
+    v.h = pl.h;
+    v.inv_h = pl.inv_h;
+    v.nx = pl.nx;
+    v.ny = pl.ny;
+    v.nz = pl.nz;
+    v.n_points = total_pts;  // positions in the shared record array are global
+    views[(size_t)i] = v;
+    centres[(size_t)i * 3 + 0] = pl.ox + 0.5 * pl.nx * pl.h;
+    centres[(size_t)i * 3 + 1] = pl.oy + 0.5 * pl.ny * pl.h;
+    centres[(size_t)i * 3 + 2] = pl.oz + 0.5 * pl.nz * pl.h;
+  }
 }
 
 void make_float4_copy(Ctx& c) {

@@ -130,25 +130,36 @@ __device__ __forceinline__ double plane_distance_rec(const Rigid& T, const Rec& 
 
 // Feed the predictor histogram of the reject kernel (reject_solve.cuh: lh_bin): one spread-out
 // atomic per planarity survivor instead of a separate pass over the distances later.
+// Feed the predictor histogram of the reject kernel (reject_solve.cuh: lh_bin): one spread-out
+// atomic per member of the statistics set instead of a separate pass over the distances later.
+// The value the atomic returns is the correspondence's rank inside its bin: it doubles as the
+// slot of a per-bin index store, so that the reject/solve kernel can read the members of the few
+// bins that hold its order statistics directly (no scan, no gather pass, no barrier).
 __device__ __forceinline__ void lin_hist_add(const DevState* st, unsigned int* lin_hist,
-                                             float planarity, double d, unsigned short* code_out) {
-  unsigned short code = LH_CODE_NONE;
+                                             float planarity, double d, unsigned int* binstore,
+                                             int bin_cap, long long qi) {
   if (lin_hist != nullptr && st->pred_valid && (double)planarity >= st->pred_minpl) {
     const int b = lh_bin(d, st->pred_med, st->pred_mad);
-    atomicAdd(&lin_hist[b], 1u);
-    code = (unsigned short)b;
+    const unsigned int slot = atomicAdd(&lin_hist[b], 1u);
+    if (binstore != nullptr && b < LH_BINS && slot < (unsigned int)bin_cap)
+      binstore[(size_t)b * bin_cap + slot] = (unsigned int)qi;
   }
-  // the bin of every member of the statistics set, kept per correspondence: the fused
-  // reject/solve kernel finds its order-statistic candidates by scanning these 2-byte codes
-  if (code_out) *code_out = code;
 }
 
 // Epilogue data of one correspondence for the fused reject/solve kernel: the matched movable
 // point in caller coordinates (so the moment pass streams it instead of chasing nn_idx ->
 // mov_xyz) and the histogram code.
 struct CorrOut {
-  unsigned short* code;  // K, may be null
-  double* m_xyz;         // K x 3, may be null
+  unsigned int* binstore;  // LH_BINS x bin_cap correspondence numbers, may be null
+  int bin_cap;
+  double* m_xyz;           // K x 3, may be null
+  // Warm start (may be null): position, in the cell-sorted record array, of the neighbour each
+  // query found in the PREVIOUS iteration of this registration.  Its distance to the moved query
+  // is a valid upper bound from the first instruction on, so most of the 27 cells of ring 1 are
+  // pruned by their distance bound before their cell-table entries are even requested.  The
+  // result is unchanged (any point is a valid bound; ties still go to the lower index).
+  uint32_t* nn_pos;
+  int warm;              // nn_pos holds positions of the previous iteration
 };
 __device__ __forceinline__ void store_matched(const CorrOut& co, long long qi, double x, double y, double z) {
   if (co.m_xyz) {
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(128)
     const float4 nr = q_nrm[i];
     const double d = plane_distance(st->T, mov_xyz, bidx, px, py, pz, nr);
     out[i] = d;
-    lin_hist_add(st, lin_hist, nr.w, d, co.code ? co.code + i : nullptr);
+    lin_hist_add(st, lin_hist, nr.w, d, co.binstore, co.bin_cap, i);
     store_matched(co, i, mov_xyz[3 * bidx + 0], mov_xyz[3 * bidx + 1], mov_xyz[3 * bidx + 2]);
   } else {
     out[i] = best;
@@ -197,13 +208,12 @@ __global__ void __launch_bounds__(128)
 // latency-bound (a handful of 32-byte L2 sectors per query), so what counts is how many of
 // those loads are in flight — with one thread per query a K = 1000 search took 27 us.
 template <int MG>
-__global__ void __launch_bounds__(128)
-    k_match_grid_coop(GridView g, const DevState* __restrict__ st, const double* __restrict__ q_xyz,
-                      const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz,
-                      long long K, int rmax, int with_distance, long long* __restrict__ nn_idx,
-                      double* __restrict__ out, unsigned int* __restrict__ unresolved,
-                      unsigned int* __restrict__ lin_hist, double cap2, CorrOut co) {
-  const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__device__ __forceinline__ void match_coop_body(
+    const GridView& g, const DevState* __restrict__ st, const double* __restrict__ q_xyz,
+    const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz, long long K, int rmax,
+    int with_distance, long long* __restrict__ nn_idx, double* __restrict__ out,
+    unsigned int* __restrict__ unresolved, unsigned int* __restrict__ lin_hist, double cap2,
+    const CorrOut& co, const long long gt) {
   const long long qi = gt / MG;
   const int sub = threadIdx.x & (MG - 1);
   if (qi >= K || st->stop) return;  // a whole group leaves together
@@ -222,6 +232,10 @@ __global__ void __launch_bounds__(128)
   long long bidx = -1;
   uint32_t bpos = 0;
   bool resolved = false;
+  if (co.warm) {
+    const uint32_t p = co.nn_pos[qi];
+    if ((long long)p < g.n_points) consider(g.recs[p], p, qx, qy, qz, best, bidx, bpos);
+  }
   for (int r = 1;; ++r) {
     const int x0 = cx - r, x1 = cx + r;
     const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
@@ -235,9 +249,16 @@ __global__ void __launch_bounds__(128)
       // issue slots as much as by latency, and 8 extra loads per lane cost more than the round
       // trip they save; profiles/README.md.)
       constexpr int NR = (8 + MG - 1) / MG;  // rows per lane in step 2
+      // distances from the query to the faces of its own cell (>= 0 up to rounding)
+      const double fxl = fmax(qx - (g.ox + cx * g.h), 0.0), fxh = fmax((g.ox + (cx + 1) * g.h) - qx, 0.0);
+      const double fyl = fmax(qy - (g.oy + cy * g.h), 0.0), fyh = fmax((g.oy + (cy + 1) * g.h) - qy, 0.0);
+      const double fzl = fmax(qz - (g.oz + cz * g.h), 0.0), fzh = fmax((g.oz + (cz + 1) * g.h) - qz, 0.0);
       {
         const int x = cx - 1 + sub;
-        const bool own = sub < 3 && x >= 0 && x < g.nx;
+        bool own = sub < 3 && x >= 0 && x < g.nx;
+        // with a warm-start bound the two side cells of the own row are usually out of reach
+        const double bx = (sub == 0) ? fxl : ((sub == 2) ? fxh : 0.0);
+        if (bx * bx > best * (1.0 + 1e-12)) own = false;
         const long long row0 = ((long long)cz * g.ny + cy) * g.nx;
         const uint32_t os = own ? cs[row0 + x] : 0u, oe = own ? cs[row0 + x + 1] : 0u;
         scan_range(g.recs, os, oe, qx, qy, qz, best, bidx, bpos);
@@ -253,10 +274,6 @@ __global__ void __launch_bounds__(128)
           bpos = op;
         }
       }
-      // distances from the query to the faces of its own cell (>= 0 up to rounding)
-      const double fxl = fmax(qx - (g.ox + cx * g.h), 0.0), fxh = fmax((g.ox + (cx + 1) * g.h) - qx, 0.0);
-      const double fyl = fmax(qy - (g.oy + cy * g.h), 0.0), fyh = fmax((g.oy + (cy + 1) * g.h) - qy, 0.0);
-      const double fzl = fmax(qz - (g.oz + cz * g.h), 0.0), fzh = fmax((g.oz + (cz + 1) * g.h) - qz, 0.0);
       const double lim = best * (1.0 + 1e-12);  // strictly farther only: ties are still visited
       uint32_t rs[NR], re[NR];
 #pragma unroll
@@ -340,6 +357,7 @@ __global__ void __launch_bounds__(128)
     if (r >= rmax) break;
   }
   if (sub != 0) return;
+  if (co.nn_pos) co.nn_pos[qi] = resolved ? bpos : 0xffffffffu;
   if (!resolved) {
     const unsigned int slot = atomicAdd(&unresolved[K], 1u);
     unresolved[slot] = (unsigned int)qi;
@@ -353,11 +371,50 @@ __global__ void __launch_bounds__(128)
     const Rec m = g.recs[bpos];
     const double d = plane_distance_rec(st->T, m, px, py, pz, nr);
     out[qi] = d;
-    lin_hist_add(st, lin_hist, nr.w, d, co.code ? co.code + qi : nullptr);
+    lin_hist_add(st, lin_hist, nr.w, d, co.binstore, co.bin_cap, qi);
     store_matched(co, qi, m.x, m.y, m.z);
   } else {
     out[qi] = best;
   }
+}
+
+template <int MG>
+__global__ void __launch_bounds__(128)
+    k_match_grid_coop(GridView g, const DevState* __restrict__ st, const double* __restrict__ q_xyz,
+                      const float4* __restrict__ q_nrm, const double* __restrict__ mov_xyz,
+                      long long K, int rmax, int with_distance, long long* __restrict__ nn_idx,
+                      double* __restrict__ out, unsigned int* __restrict__ unresolved,
+                      unsigned int* __restrict__ lin_hist, double cap2, CorrOut co) {
+  match_coop_body<MG>(g, st, q_xyz, q_nrm, mov_xyz, K, rmax, with_distance, nn_idx, out, unresolved,
+                      lin_hist, cap2, co, blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+
+// Batched form: blockIdx.y is the pair, everything else comes from its descriptor.  The ring
+// expansion runs to completion (no brute-force hand-over inside a batch).
+struct BatchMatchArgs {
+  const PairDev* pairs;
+  const DevState* state;
+  const double* q_xyz;
+  const float4* q_nrm;
+  long long* nn_idx;
+  double* dist;
+  unsigned int* lin_hist;
+  unsigned int* binstore;
+  int bin_cap;
+  double* m_xyz;
+  uint32_t* nn_pos;
+  int warm;
+};
+template <int MG>
+__global__ void __launch_bounds__(128) k_match_batch(BatchMatchArgs a) {
+  const PairDev pd = a.pairs[blockIdx.y];
+  const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (gt / MG >= pd.K) return;
+  const long long q = pd.q_off;
+  const CorrOut co{a.binstore + (size_t)blockIdx.y * LH_BINS * a.bin_cap, a.bin_cap, a.m_xyz + 3 * q, a.nn_pos + q, a.warm};
+  match_coop_body<MG>(pd.gmov, a.state + blockIdx.y, a.q_xyz + 3 * q, a.q_nrm + q, nullptr, pd.K, 1 << 30, 1,
+                      a.nn_idx + q, a.dist + q, nullptr, a.lin_hist + (size_t)blockIdx.y * (LH_BINS + 2), -1.0,
+                      co, gt);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -625,7 +682,7 @@ __global__ void __launch_bounds__(128)
     const float4 nr = q_nrm[q];
     const double dd = plane_distance(T, mov_xyz, ix, q_xyz[3 * q + 0], q_xyz[3 * q + 1], q_xyz[3 * q + 2], nr);
     out[q] = dd;
-    lin_hist_add(st, lin_hist, nr.w, dd, co.code ? co.code + q : nullptr);
+    lin_hist_add(st, lin_hist, nr.w, dd, co.binstore, co.bin_cap, q);
     store_matched(co, q, mov_xyz[3 * ix + 0], mov_xyz[3 * ix + 1], mov_xyz[3 * ix + 2]);
   } else {
     out[q] = d;
@@ -657,10 +714,24 @@ void gather_queries_launch(Ctx& c) {
   c.tm.kernel_launches += 1;
 }
 
+// Slots per histogram bin of the per-bin index store: a few times the mean count of a bin that
+// matters (the statistics set spreads over ~2500 of the 4096 bins), so that a distribution which
+// narrows several-fold between two iterations still fits; a bin that overflows just sends that
+// iteration through the general kernel.
+int bin_cap_for(long long K) {
+  long long cap = 32;
+  while (cap < K / 192 && cap < 2048) cap *= 2;
+  return (int)cap;
+}
+static void reserve_binstore(Ctx& c) {
+  c.bin_cap = bin_cap_for(c.K);
+  c.binstore.reserve((size_t)LH_BINS * c.bin_cap);
+}
+
 // Brute-force pass over either the unresolved list (qlist != nullptr) or all K queries.
 static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
   if (with_distance) {
-    c.corr_code.reserve(std::max<long long>(c.K, 1));
+    reserve_binstore(c);
     c.m_xyz.reserve(3 * std::max<long long>(c.K, 1));
   }
   // the attribute belongs to the (device-specific) function handle: once per context, not per process
@@ -692,9 +763,68 @@ static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
   k_bf_finalize<<<(unsigned)((q_total + 127) / 128), 128, 0, c.stream>>>(
       partials, n_chunks, q_total, qlist, qcount, c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p,
       with_distance ? 1 : 0, c.nn_idx.p, out, with_distance ? c.lin_hist.p : nullptr,
-      with_distance ? CorrOut{c.corr_code.p, c.m_xyz.p} : CorrOut{nullptr, nullptr});
+      with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, nullptr, 0} : CorrOut{nullptr, 0, nullptr, nullptr, 0});
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 2;
+}
+
+namespace {
+// per pair: sel[i] = rint(linspace(0, n_fix - 1, K)) (PointCloud.select_n_points, k_select_n in
+// capi.cu) and the gather of the selected fixed points, in one launch for the whole batch
+__global__ void __launch_bounds__(256)
+    k_select_gather_batch(const PairDev* __restrict__ pairs, const double* __restrict__ fix_xyz, int away,
+                          long long* __restrict__ sel, double* __restrict__ q_xyz) {
+  const PairDev pd = pairs[blockIdx.y];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= pd.K) return;
+  const long long m = pd.n_fix, n = pd.K;
+  long long j = i;
+  if (n < m) {
+    const double step = (n > 1) ? (double)(m - 1) / (double)(n - 1) : 0.0;
+    const double y = (i == n - 1 && n > 1) ? (double)(m - 1) : (double)i * step;
+    j = (long long)(away ? round(y) : rint(y));
+  }
+  sel[pd.q_off + i] = j;
+  const double* __restrict__ src = fix_xyz + 3 * (pd.fix_off + j);
+  double* __restrict__ dst = q_xyz + 3 * (pd.q_off + i);
+  dst[0] = src[0];
+  dst[1] = src[1];
+  dst[2] = src[2];
+}
+}  // namespace
+
+void batch_select_gather_launch(Ctx& c, Batch& b, long long correspondences, int round_away) {
+  (void)correspondences;
+  k_select_gather_batch<<<dim3((unsigned)((b.Kmax + 255) / 256), b.n_pairs), 256, 0, c.stream>>>(
+      b.pairs.p, b.fix_xyz.p, round_away, b.sel_idx.p, b.q_xyz.p);
+  SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
+}
+
+void batch_match_launch(Ctx& c, Batch& b, bool warm) {
+  BatchMatchArgs a;
+  a.pairs = b.pairs.p;
+  a.state = b.state.p;
+  a.q_xyz = b.q_xyz.p;
+  a.q_nrm = b.q_nrm.p;
+  a.nn_idx = b.nn_idx.p;
+  a.dist = b.dist.p;
+  a.lin_hist = b.lin_hist.p;
+  a.binstore = b.binstore.p;
+  a.bin_cap = b.bin_cap;
+  a.m_xyz = b.m_xyz.p;
+  a.nn_pos = b.nn_pos.p;
+  a.warm = warm ? 1 : 0;
+  // lanes per query as in the single-pair launch, by the number of queries in flight
+  const long long total = b.Kmax * b.n_pairs;
+  int mg = c.match_group;
+  if (mg == 0 || mg == 1) mg = (total <= 16384) ? 16 : ((total <= 65536) ? 8 : 4);
+  const dim3 grid((unsigned)((b.Kmax * mg + 127) / 128), b.n_pairs);
+  if (mg == 4) k_match_batch<4><<<grid, 128, 0, c.stream>>>(a);
+  else if (mg == 8) k_match_batch<8><<<grid, 128, 0, c.stream>>>(a);
+  else k_match_batch<16><<<grid, 128, 0, c.stream>>>(a);
+  SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
 }
 
 void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, bool allow_bf, double cap2) {
@@ -710,9 +840,16 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   c.nn_idx.reserve(K);
   c.dist.reserve(K);
   c.unresolved.reserve(K + 1);
-  c.corr_code.reserve(std::max<long long>(K, 1));
+  reserve_binstore(c);
   c.m_xyz.reserve(3 * std::max<long long>(K, 1));
-  const CorrOut co = with_distance ? CorrOut{c.corr_code.p, c.m_xyz.p} : CorrOut{nullptr, nullptr};
+  c.nn_pos.reserve(std::max<long long>(K, 1));
+  const bool warm = with_distance && c.warm_start && c.nn_pos_valid && c.nn_pos_K == K;
+  const CorrOut co = with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, c.nn_pos.p, warm ? 1 : 0}
+                                   : CorrOut{nullptr, 0, nullptr, nullptr, 0};
+  if (with_distance) {
+    c.nn_pos_valid = (c.nn_engine != SICP_NN_BRUTE) && c.match_group != 1;
+    c.nn_pos_K = K;
+  }
   double* out = with_distance ? c.dist.p : out_d2;
   if (c.nn_engine == SICP_NN_BRUTE) {
     bf_launch(c, with_distance, out, true);

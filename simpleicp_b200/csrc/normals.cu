@@ -110,11 +110,11 @@ __device__ void grid_knn(const GridView& g, double qx, double qy, double qz, Top
   }
 }
 
-__global__ void __launch_bounds__(128)
-    k_knn_pca(GridView g, const double* __restrict__ fix_xyz, const double* __restrict__ q_xyz,
-              long long K, int k, int sign_mode, float4* __restrict__ q_nrm,
-              long long* __restrict__ knn_idx, double* __restrict__ knn_d2) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__device__ __forceinline__ void knn_pca_body(const GridView& g, const double* __restrict__ fix_xyz,
+                                             const double* __restrict__ q_xyz, long long K, int k,
+                                             int sign_mode, float4* __restrict__ q_nrm,
+                                             long long* __restrict__ knn_idx,
+                                             double* __restrict__ knn_d2, const long long i) {
   if (i >= K) return;
   const double qx = q_xyz[3 * i + 0], qy = q_xyz[3 * i + 1], qz = q_xyz[3 * i + 2];
   TopK tk;
@@ -169,6 +169,23 @@ __global__ void __launch_bounds__(128)
   q_nrm[i] = o;
 }
 
+__global__ void __launch_bounds__(128)
+    k_knn_pca(GridView g, const double* __restrict__ fix_xyz, const double* __restrict__ q_xyz,
+              long long K, int k, int sign_mode, float4* __restrict__ q_nrm,
+              long long* __restrict__ knn_idx, double* __restrict__ knn_d2) {
+  knn_pca_body(g, fix_xyz, q_xyz, K, k, sign_mode, q_nrm, knn_idx, knn_d2,
+               blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+
+// batched: blockIdx.y = pair; neighbour indices are local to the pair's fixed cloud
+__global__ void __launch_bounds__(128)
+    k_knn_pca_batch(const PairDev* __restrict__ pairs, const double* __restrict__ fix_xyz,
+                    const double* __restrict__ q_xyz, int k, int sign_mode, float4* __restrict__ q_nrm) {
+  const PairDev pd = pairs[blockIdx.y];
+  knn_pca_body(pd.gfix, fix_xyz + 3 * pd.fix_off, q_xyz + 3 * pd.q_off, pd.K, k, sign_mode,
+               q_nrm + pd.q_off, nullptr, nullptr, blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+
 }  // namespace
 
 void estimate_normals_launch(Ctx& c, int k) {
@@ -183,6 +200,15 @@ void estimate_normals_launch(Ctx& c, int k) {
   k_knn_pca<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(
       c.gfix.view(), c.fix_xyz.p, c.q_xyz.p, c.K, k, c.sign_mode, c.q_nrm.p, c.knn_idx.p,
       c.knn_d2.p);
+  SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
+}
+
+void batch_normals_launch(Ctx& c, Batch& b, int k) {
+  SICP_REQUIRE(k >= 2 && k <= kMaxK, SICP_ERR_BAD_ARG,
+               "neighbors must be between 2 and 64 (got " + std::to_string(k) + ")");
+  k_knn_pca_batch<<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
+      b.pairs.p, b.fix_xyz.p, b.q_xyz.p, k, c.sign_mode, b.q_nrm.p);
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 1;
 }

@@ -1301,9 +1301,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
 // that 147 SMs wait for (profiles/r1_phase_timeline.md).  Here every dependency is resolved by
 // construction instead of by waiting:
 //   select     every block derives median and MAD ITSELF from the predictor histogram the match
-//              kernel filled plus a scan of the 2-byte bin codes it stored per correspondence
-//              (200 KB at K = 100 000, L2 resident): redundant, identical work on every SM, no
-//              exchange.  Same exact order statistics as predicted_median_mad().
+//              kernel filled and the per-bin index store it filled with the same atomic (slot =
+//              returned count): the few hundred members of the bins that hold the order
+//              statistics are read directly — redundant, identical work on every SM, no exchange,
+//              no pass over the K correspondences.  (A first version scanned a 2-byte bin code per
+//              correspondence in every block: 38 us of 2 M thread-instructions per SM.)  Same exact
+//              order statistics as predicted_median_mad().
 //   accumulate each block streams its share of (normal, distance, matched point, fixed point) —
 //              the match kernel stored the matched point, so there is no index chase — and
 //              writes keep flags and per-block partial sums.
@@ -1323,8 +1326,6 @@ constexpr int RSF_NPART = 3 * RSF_NACC;  // partial sums per block
 
 struct SharedF {
   Shared s;
-  unsigned int cidx[2][RS_CAP];  // correspondences in the median bins / the MAD bracket
-  unsigned int n_cand[2];
   double redf[RS_WARPS][RSF_NACC];
   double totf[RSF_NPART];
   double m1[13];  // sum phi
@@ -1332,8 +1333,32 @@ struct SharedF {
 };
 
 // Plan + gather + selection; true on success (median, mad, n1 set; n1 == 0 is a success).
+// k-th smallest (0-based) and its successor among n <= RS_THREADS keys in shared memory by direct
+// ranking: one candidate per thread, n broadcast reads — two block barriers instead of the eight
+// radix passes block_select() needs when the keys share their leading bytes (they always do here:
+// the candidates come from a handful of adjacent histogram bins).
+__device__ __forceinline__ void rank_select(Shared& s, const unsigned long long* keys, int n, unsigned int k,
+                                            unsigned long long& klo, unsigned long long& khi) {
+  const int tid = threadIdx.x;
+  if (tid < n) {
+    const unsigned long long key = keys[tid];
+    unsigned int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const unsigned long long kj = keys[j];
+      r += (kj < key || (kj == key && j < tid)) ? 1u : 0u;
+    }
+    if (r == k) s.small[0] = key;
+    if (r == k + 1u) s.small[1] = key;
+  }
+  __syncthreads();
+  klo = s.small[0];
+  khi = (k + 1u < (unsigned int)n) ? s.small[1] : ~0ull;
+  __syncthreads();
+}
+
+#define RSF_STAMP(i) do { if (bid == 0 && tid == 0) wk.phase_t[i] = global_timer_ns(); } while (0)
 __device__ bool fused_select(SharedF& sf, const RSArgs& a, RSWork wk, const DevState* st,
-                             unsigned int& n1_out, double& median, double& mad) {
+                             unsigned int& n1_out, double& median, double& mad, const int G, const int bid) {
   Shared& s = sf.s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int PER = (LH_BINS + RS_THREADS - 1) / RS_THREADS;
@@ -1351,7 +1376,6 @@ __device__ bool fused_select(SharedF& sf, const RSArgs& a, RSWork wk, const DevS
     if (lane >= o) incl += t;
   }
   if (lane == 31) s.scan_tmp[warp] = incl;
-  if (tid < 2) sf.n_cand[tid] = 0;
   __syncthreads();
   unsigned int woff = 0, total_in = 0;
   for (int i = 0; i < RS_WARPS; ++i) {
@@ -1428,55 +1452,58 @@ __device__ bool fused_select(SharedF& sf, const RSArgs& a, RSWork wk, const DevS
   const unsigned int cnt_edge = Nin(e_hi) - n_inner;
   if (cnt_edge > (unsigned int)(RS_CAP - 2) || k < n_inner || k2 - n_inner >= cnt_edge) return false;
   const unsigned int kM = k - n_inner;
+  RSF_STAMP(10);
 
-  // ---- scan the 2-byte codes of all K correspondences (vector loads of 8 codes)
+  // ---- read the members of the candidate bins from the per-bin index store the match kernel
+  // filled (slot = the value its histogram atomic returned): no scan, no gather pass.  A bin with
+  // more members than slots means the distribution narrowed a lot since the last iteration: that
+  // iteration goes through the general path.
   {
-    const unsigned short* __restrict__ code = a.code;
-    const long long K = a.K;
-    auto visit = [&](unsigned int c, long long i) {
-      if (c < (unsigned int)LH_BINS) {
-        const int b = (int)c;
-        const int delta = (b < bm) ? (bm - b) : ((b > bm2) ? (b - bm2) : 0);
-        if (delta == 0) {
-          const unsigned int p = atomicAdd(&sf.n_cand[0], 1u);
-          if (p < (unsigned int)RS_CAP) sf.cidx[0][p] = (unsigned int)i;
-        }
-        if (delta >= e_lo && delta <= e_hi) {
-          const unsigned int p = atomicAdd(&sf.n_cand[1], 1u);
-          if (p < (unsigned int)RS_CAP) sf.cidx[1][p] = (unsigned int)i;
-        }
-      }
-    };
-    const bool aligned = (reinterpret_cast<uintptr_t>(code) & 15) == 0;
-    const long long nvec = aligned ? (K >> 3) : 0;
-    const uint4* __restrict__ c4 = reinterpret_cast<const uint4*>(code);
-    for (long long q = tid; q < nvec; q += RS_THREADS) {
-      const uint4 w = __ldcg(c4 + q);
-      const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        visit(ww[j] & 0xffffu, q * 8 + 2 * j);
-        visit(ww[j] >> 16, q * 8 + 2 * j + 1);
-      }
+    const int cap = a.bin_cap;
+    int over = 0;
+    const int lo_b = bm - e_hi, hi_b = bm2 + e_hi;
+    for (int bb = lo_b + tid; bb <= hi_b; bb += RS_THREADS) {
+      const int delta = (bb < bm) ? (bm - bb) : ((bb > bm2) ? (bb - bm2) : 0);
+      if ((delta == 0 || (delta >= e_lo && delta <= e_hi)) && P[bb] - ((bb > 0) ? P[bb - 1] : 0u) > (unsigned int)cap)
+        over = 1;
     }
-    for (long long i = nvec * 8 + tid; i < K; i += RS_THREADS) visit((unsigned int)__ldcg(code + i), i);
+    if (__syncthreads_or(over)) return false;
   }
-  __syncthreads();
-  // the codes and the histogram come from the same match pass: anything else is a stale buffer
-  if (sf.n_cand[0] != cnt_med || sf.n_cand[1] != cnt_edge) return false;
+  // position (in histogram order) -> (bin, slot) -> correspondence number
+  auto member = [&](unsigned int pos) -> unsigned int {
+    int lo = 0, hi = LH_BINS - 1;  // first bin with P[bin] > pos
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (P[mid] > pos) hi = mid; else lo = mid + 1;
+    }
+    const unsigned int slot = pos - ((lo > 0) ? P[lo - 1] : 0u);
+    return __ldcg(a.binstore + (size_t)lo * a.bin_cap + slot);
+  };
+  const unsigned int edge_lo_start = (bm - e_hi > 0) ? P[bm - e_hi - 1] : 0u;
+  const int el = max(e_lo, 1);
+  // members of the low edge window [bm - e_hi, bm - el]; with e_lo == 0 the window runs through
+  // the median bins to bm2 + e_hi in one piece
+  const unsigned int c_low = (e_lo == 0) ? cnt_edge : (P[bm - el] - edge_lo_start);
+  const unsigned int edge_hi_start = P[bm2 + el - 1];
+  RSF_STAMP(11);
   unsigned long long klo, khi;
-  for (int t = tid; t < (int)cnt_med; t += RS_THREADS) s.sortbuf[t] = f64_to_key(__ldcg(a.dist + sf.cidx[0][t]));
+  for (int t = tid; t < (int)cnt_med; t += RS_THREADS) s.sortbuf[t] = f64_to_key(__ldcg(a.dist + member(below_m + t)));
   __syncthreads();
-  block_select(s, s.sortbuf, (int)cnt_med, kA, 64, ~0ull, klo, khi);
+  if (cnt_med <= (unsigned int)RS_THREADS) rank_select(s, s.sortbuf, (int)cnt_med, kA, klo, khi);
+  else block_select(s, s.sortbuf, (int)cnt_med, kA, 64, ~0ull, klo, khi);
   median = even ? (a.variant ? key_to_f64(khi) : 0.5 * (key_to_f64(klo) + key_to_f64(khi))) : key_to_f64(klo);
   __syncthreads();
-  for (int t = tid; t < (int)cnt_edge; t += RS_THREADS)
-    s.sortbuf[t] = f64_to_key(fabs(__ldcg(a.dist + sf.cidx[1][t]) - median));
+  RSF_STAMP(12);
+  for (int t = tid; t < (int)cnt_edge; t += RS_THREADS) {
+    const unsigned int pos = ((unsigned int)t < c_low) ? edge_lo_start + t : edge_hi_start + (t - c_low);
+    s.sortbuf[t] = f64_to_key(fabs(__ldcg(a.dist + member(pos)) - median));
+  }
   __syncthreads();
-  block_select(s, s.sortbuf, (int)cnt_edge, kM, 64, ~0ull, klo, khi);
+  if (cnt_edge <= (unsigned int)RS_THREADS) rank_select(s, s.sortbuf, (int)cnt_edge, kM, klo, khi);
+  else block_select(s, s.sortbuf, (int)cnt_edge, kM, 64, ~0ull, klo, khi);
   mad = even ? (a.variant ? key_to_f64(khi) : 0.5 * (key_to_f64(klo) + key_to_f64(khi))) : key_to_f64(klo);
   __syncthreads();
-  if (blockIdx.x == 0 && tid == 0) {
+  if (bid == 0 && tid == 0) {
     wk.phase_t[26] = cnt_med;
     wk.phase_t[27] = cnt_edge;
   }
@@ -1492,24 +1519,36 @@ __device__ __forceinline__ double theta_entry(const Rigid& T, const double* cm, 
   return T.r[r * 3 + 0] * cm[0] + T.r[r * 3 + 1] * cm[1] + T.r[r * 3 + 2] * cm[2] + T.t[r] - cf[r];
 }
 
-__global__ void __launch_bounds__(RS_THREADS, 1) k_rs_fused(RSArgs a, RSWork wk) {
-  extern __shared__ __align__(16) unsigned char rsf_smem[];
-  SharedF& sf = *reinterpret_cast<SharedF*>(rsf_smem);
+__device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int bid, SharedF& sf) {
   Shared& s = sf.s;
   DevState* st = a.state;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long K = a.K;
-  const int G = gridDim.x;
   if (st->stop) return;  // a previous iteration met the stop rule (or asked for a re-run)
-  RS_STAMP(0);
+  RSF_STAMP(0);
 
   // ---- select (every block, identical result)
   unsigned int n1 = 0;
   double median = 0.0, mad = 0.0;
   bool ok = a.hist_expected && st->pred_valid && st->pred_minpl == a.stat_minpl && st->pred_mad > 0.0;
-  if (ok) ok = fused_select(sf, a, wk, st, n1, median, mad);
+  if (ok) ok = fused_select(sf, a, wk, st, n1, median, mad, G, bid);
+  if (!ok && G == 1) {
+    // a single block owns the whole problem (K <= 4096, or one pair of a batch): no prediction —
+    // first iteration, large change — simply means the radix selection, here and now
+    __syncthreads();
+    radix_median<false, 0>(s, a, wk, 0.0, n1);
+    if (n1 != 0) {
+      median = a.variant ? s.bc[1] : 0.5 * (s.bc[0] + s.bc[1]);
+      __syncthreads();
+      unsigned int n1b = 0;
+      radix_median<false, 1>(s, a, wk, median, n1b);
+      mad = a.variant ? s.bc[1] : 0.5 * (s.bc[0] + s.bc[1]);
+    }
+    __syncthreads();
+    ok = true;
+  }
   const double lim = a.variant ? 3.0 * (1.4826 * mad) : 3.0 * mad;
-  RS_STAMP(2);
+  RSF_STAMP(2);
 
   // ---- accumulate this block's share
   const Rigid Tin = st->T;
@@ -1521,7 +1560,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_rs_fused(RSArgs a, RSWork wk)
 #pragma unroll
     for (int j = 0; j < RSF_NACC; ++j) acc[j] = 0.0;
     const long long chunk = (K + G - 1) / G;
-    const long long i0 = blockIdx.x * chunk, i1 = min(i0 + chunk, K);
+    const long long i0 = bid * chunk, i1 = min(i0 + chunk, K);
     const float4* __restrict__ qn = a.q_nrm;
     const double* __restrict__ dd = a.dist;
     const double* __restrict__ mv = a.m_xyz;
@@ -1596,10 +1635,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_rs_fused(RSArgs a, RSWork wk)
       const int r = tid / RSF_NACC, j = tid % RSF_NACC;
       double vv = 0.0;
       for (int ww = r; ww < RS_WARPS; ww += 3) vv += sf.redf[ww][j];
-      wk.partials[(size_t)tid * G + blockIdx.x] = vv;
+      wk.partials[(size_t)tid * G + bid] = vv;
     }
   }
-  RS_STAMP(3);
+  RSF_STAMP(3);
 
   // ---- ticket: the last block to arrive owns the serial part
   __threadfence();
@@ -1811,6 +1850,134 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_rs_fused(RSArgs a, RSWork wk)
   }
 }
 
+__global__ void __launch_bounds__(RS_THREADS, 1) k_rs_fused(RSArgs a, RSWork wk) {
+  extern __shared__ __align__(16) unsigned char rsf_smem[];
+  rs_fused_body(a, wk, gridDim.x, blockIdx.x, *reinterpret_cast<SharedF*>(rsf_smem));
+}
+
+// Batched form: one block per pair, every per-query pointer offset by the pair's q_off.
+struct BatchRsArgs {
+  RSArgs proto;  // shared parameters; per-query pointers are the batch arrays' bases
+  const PairDev* pairs;
+  DevState* state;
+  sicp_iter_record* rec;  // n_pairs x rec_stride
+  int rec_stride;
+  unsigned int* lin_hist;
+  double* partials;
+  unsigned int* ticket;
+  unsigned long long* phase_t;
+};
+__global__ void __launch_bounds__(RS_THREADS, 1) k_rs_batch(BatchRsArgs b) {
+  extern __shared__ __align__(16) unsigned char rsf_smem[];
+  const int pair = blockIdx.x;
+  const PairDev& pd = b.pairs[pair];
+  RSArgs a = b.proto;
+  const long long q = pd.q_off;
+  a.K = pd.K;
+  a.dist += q;
+  a.q_nrm += q;
+  a.q_xyz += 3 * q;
+  a.keep += q;
+  a.binstore += (size_t)pair * LH_BINS * a.bin_cap;
+  a.m_xyz += 3 * q;
+  a.state = b.state + pair;
+  a.rec = b.rec + (size_t)pair * b.rec_stride + a.it;
+  a.cm[0] = pd.cm[0];
+  a.cm[1] = pd.cm[1];
+  a.cm[2] = pd.cm[2];
+  RSWork wk{};
+  wk.lin_hist = b.lin_hist + (size_t)pair * (LH_BINS + 2);
+  wk.partials = b.partials + (size_t)pair * RSF_NPART;
+  wk.ticket = b.ticket + pair;
+  wk.phase_t = b.phase_t + (size_t)pair * 32;
+  rs_fused_body(a, wk, 1, 0, *reinterpret_cast<SharedF*>(rsf_smem));
+}
+
+// End of a batched run, one block per pair: residuals of the kept correspondences at the final
+// transform (reference operation order), their exact two-pass mean / std, and the result record.
+__global__ void __launch_bounds__(256)
+    k_finish_batch(const PairDev* __restrict__ pairs, const DevState* __restrict__ state,
+                   const uint8_t* __restrict__ keep, const double* __restrict__ m_xyz,
+                   const double* __restrict__ q_xyz, const float4* __restrict__ q_nrm, int variant,
+                   int max_iterations, sicp_pair_result* __restrict__ out) {
+  const int pair = blockIdx.x;
+  const PairDev& pd = pairs[pair];
+  const DevState& st = state[pair];
+  const long long q = pd.q_off, K = pd.K;
+  __shared__ double sh[8];
+  __shared__ double mean_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Rigid Tn = st.T_res;
+  const bool have = st.iterations_done > 0;
+  auto resid_of = [&](long long i) {
+    double tx, ty, tz;
+    rigid_apply(Tn, m_xyz[3 * (q + i) + 0], m_xyz[3 * (q + i) + 1], m_xyz[3 * (q + i) + 2], tx, ty, tz);
+    const float4 nr = q_nrm[q + i];
+    const double dx = tx - q_xyz[3 * (q + i) + 0], dy = ty - q_xyz[3 * (q + i) + 1], dz = tz - q_xyz[3 * (q + i) + 2];
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, (double)nr.x), __dmul_rn(dy, (double)nr.y)), __dmul_rn(dz, (double)nr.z));
+  };
+  double acc = 0.0, cnt = 0.0;
+  if (have)
+    for (long long i = threadIdx.x; i < K; i += 256)
+      if (keep[q + i]) {
+        acc += resid_of(i);
+        cnt += 1.0;
+      }
+  acc = warp_sum(acc);
+  cnt = warp_sum(cnt);
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    mean_s = t;
+  }
+  __syncthreads();
+  // (count reduced the same way)
+  if (lane == 0) sh[warp] = cnt;
+  __syncthreads();
+  double n = 0.0;
+  for (int i = 0; i < 8; ++i) n += sh[i];
+  const double mean = (n > 0.0) ? mean_s / n : nan("");
+  __syncthreads();
+  acc = 0.0;
+  if (have)
+    for (long long i = threadIdx.x; i < K; i += 256)
+      if (keep[q + i]) {
+        const double d = resid_of(i) - mean;
+        acc = fma(d, d, acc);
+      }
+  acc = warp_sum(acc);
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    sicp_pair_result r;
+    r.iterations = st.iterations_done;
+    r.converged = (st.stop == 1) ? 1 : 0;
+    r.reserved = 0;
+    r.n_kept = st.n_kept;
+    // fewer than 6 correspondences at some iteration (stop 2, or an iteration that never finished)
+    const bool too_few = (st.stop == 2) || (!st.stop && st.iterations_done < max_iterations) || !have;
+    r.status = too_few ? SICP_ERR_TOO_FEW_CORR : (st.lm_ok ? SICP_OK : SICP_ERR_SINGULAR);
+    const Rigid& H = variant ? st.H_rep : st.T;
+    for (int a = 0; a < 3; ++a) {
+      for (int c2 = 0; c2 < 3; ++c2) r.H[a * 4 + c2] = H.r[a * 3 + c2];
+      r.H[a * 4 + 3] = H.t[a];
+    }
+    r.H[12] = r.H[13] = r.H[14] = 0.0;
+    r.H[15] = 1.0;
+    for (int j = 0; j < 6; ++j) {
+      r.x[j] = variant ? st.x_new[j] : st.x[j];
+      r.sigma[j] = st.sigma[j];
+    }
+    r.mean_res = mean;
+    r.std_res = (n > 0.0) ? (variant ? sqrt(t / (n - 1.0)) : sqrt(t / n)) : nan("");
+    out[pair] = r;
+  }
+}
+
 // Residual vector of the LAST iteration (reference operation order, optimization.py:117-124) for
 // the kept correspondences, from the matched points the match kernel stored.  One launch after
 // the loop; the compaction and the exact two-pass statistics follow (k_resid_stats).
@@ -2019,7 +2186,8 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
 void rs_fused_launch(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, int rec_slot,
                      bool want_sigma) {
   const long long K = c.K;
-  const int G = (int)std::min<long long>(c.num_sms, std::max<long long>(1, (K + 767) / 768));
+  // K <= 4096: a single block (it never needs the host's re-run protocol, see rs_fused_body)
+  const int G = (K <= 4096) ? 1 : (int)std::min<long long>(c.num_sms, std::max<long long>(1, (K + 767) / 768));
   if (!c.rsf_attr_set) {
     SICP_CUDA(cudaFuncSetAttribute(k_rs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(SharedF)));
@@ -2060,7 +2228,8 @@ void rs_fused_launch(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, in
   a.arm_stop = arm_stop ? 1 : 0;
   a.hist_expected = c.lin_hist_pending ? 1 : 0;
   c.lin_hist_pending = false;  // the kernel leaves the histogram zeroed
-  a.code = c.corr_code.p;
+  a.binstore = c.binstore.p;
+  a.bin_cap = c.bin_cap;
   a.m_xyz = c.m_xyz.p;
   a.want_sigma = want_sigma ? 1 : 0;
   RSWork wk{};
@@ -2069,6 +2238,55 @@ void rs_fused_launch(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, in
   wk.lin_hist = c.lin_hist.p;
   wk.ticket = c.rsf_ticket.p;
   k_rs_fused<<<G, RS_THREADS, sizeof(SharedF), c.stream>>>(a, wk);
+  SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
+}
+
+void batch_rs_launch(Ctx& c, Batch& b, const sicp_run_params& p, int it, bool want_sigma) {
+  if (!c.rsb_attr_set) {
+    SICP_CUDA(cudaFuncSetAttribute(k_rs_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedF)));
+    c.rsb_attr_set = true;
+  }
+  BatchRsArgs ba;
+  RSArgs& a = ba.proto;
+  a = RSArgs{};
+  a.dist = b.dist.p;
+  a.q_nrm = b.q_nrm.p;
+  a.q_xyz = b.q_xyz.p;
+  a.keep = b.keep.p;
+  a.binstore = b.binstore.p;
+  a.bin_cap = b.bin_cap;
+  a.m_xyz = b.m_xyz.p;
+  a.min_planarity = p.min_planarity;
+  a.variant = c.variant;
+  a.stat_minpl = c.variant ? -kInf : p.min_planarity;
+  a.min_change = p.min_change;
+  a.w_param = p.lsq.distance_weight;
+  for (int j = 0; j < 6; ++j) {
+    a.obs[j] = p.lsq.observed[j];
+    a.wobs[j] = p.lsq.obs_weight[j];
+  }
+  a.it = it;
+  a.do_solve = 1;
+  a.arm_stop = 1;
+  a.hist_expected = 1;  // every batched match feeds the per-pair histogram (when its predictor is valid)
+  a.want_sigma = want_sigma ? 1 : 0;
+  ba.pairs = b.pairs.p;
+  ba.state = b.state.p;
+  ba.rec = b.rec.p;
+  ba.rec_stride = p.max_iterations;
+  ba.lin_hist = b.lin_hist.p;
+  ba.partials = b.partials.p;
+  ba.ticket = b.ticket.p;
+  ba.phase_t = b.phase_t.p;
+  k_rs_batch<<<b.n_pairs, RS_THREADS, sizeof(SharedF), c.stream>>>(ba);
+  SICP_CUDA(cudaGetLastError());
+  c.tm.kernel_launches += 1;
+}
+
+void batch_finish_launch(Ctx& c, Batch& b, int max_iterations) {
+  k_finish_batch<<<b.n_pairs, 256, 0, c.stream>>>(b.pairs.p, b.state.p, b.keep.p, b.m_xyz.p, b.q_xyz.p, b.q_nrm.p,
+                                                  c.variant, max_iterations, b.results.p);
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 1;
 }

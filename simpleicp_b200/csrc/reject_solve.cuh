@@ -44,7 +44,6 @@ struct DevState {
 // counter.  The bin function is monotone non-decreasing in d, which is all the exactness of the
 // selection needs; both sides evaluate this very expression.
 constexpr int LH_BINS = 4096;
-constexpr unsigned short LH_CODE_NONE = 0xFFFFu;  // correspondence outside the statistics set
 __host__ __device__ inline int lh_bin(double d, double med, double mad) {
   const double lo = med - 4.0 * mad;
   const double inv_w = (double)LH_BINS / (8.0 * mad);
@@ -79,7 +78,8 @@ struct RSArgs {
   int variant;        // sicp_variant
   double stat_minpl;  // planarity bound of the set the median/MAD are taken over (-inf: everybody)
   // fused kernel only (k_rs_fused): what the match kernels left per correspondence
-  const unsigned short* code;  // predictor-histogram bin, LH_CODE_NONE outside the statistics set
+  const unsigned int* binstore;  // LH_BINS x bin_cap: correspondence numbers per predictor-histogram bin
+  int bin_cap;
   const double* m_xyz;         // matched movable point (caller coordinates), K x 3
   int want_sigma;              // evaluate the parameter sigmas even if the stop rule does not fire
 };

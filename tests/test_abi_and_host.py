@@ -246,3 +246,18 @@ def test_batch_gloo_world2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_synthetic_generators_equal_the_oracles():
+    """bench.py's product arm takes its inputs from simpleicp_b200.synthetic (no oracle import);
+    the arrays are the oracle's bit for bit, so both arms see the same workload."""
+    from simpleicp_b200 import synthetic
+
+    a, b = synthetic.c3_pair(3000), O.c3_pair(3000)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    Xf, Xm, H = synthetic.c5_pair(3, 2000)
+    assert np.array_equal(Xf, O.surface(2000, 10_006, extent=30.0))
+    assert np.array_equal(Xm, O.transform_by_H(O.surface(2000, 10_007, extent=30.0), np.linalg.inv(H)))
+    src = (REPO / "bench.py").read_text()
+    b200_arm = src[src.index("def run_b200"):src.index("# ---- CPU baseline beside it")]
+    assert "oracle" not in b200_arm  # only the cpu_baseline / parity legs of bench.py touch oracle/

@@ -527,8 +527,11 @@ def test_batch_of_pairs_matches_individual_runs(gpu):
         Ht = O.rbp_to_H([0.004 * (i + 1), -0.003, 0.005, 0.05, -0.03 * i, 0.02])
         Xm = O.transform_by_H(O.surface(40_000, 10_001 + 2 * i, extent=30.0), np.linalg.inv(Ht))
         pairs.append((Xf, Xm))
-    table = sb.simpleicp_batch(pairs, concurrency=3)
+    table = sb.simpleicp_batch(pairs, concurrency=3, engine="pool")
     assert table.shape == (6, 20)
+    table_b = sb.simpleicp_batch(pairs)  # batched engine
+    np.testing.assert_allclose(table_b[:, :16], table[:, :16], rtol=0, atol=1e-12)
+    assert np.array_equal(table_b[:, 16:18], table[:, 16:18])
     for i, (Xf, Xm) in enumerate(pairs):
         r = sb.register(Xf, Xm)
         np.testing.assert_allclose(table[i, :16].reshape(4, 4), r.H, rtol=0, atol=1e-12)
@@ -750,3 +753,77 @@ def test_barrier_free_kernel_equals_cooperative_kernel(gpu, name, kw):
     # the last record carries the exact two-pass statistics of the returned residual vector
     np.testing.assert_allclose(a.records[-1]["mean_res"], a.residuals.mean(), rtol=0, atol=1e-15)
     np.testing.assert_allclose(a.records[-1]["std_res"], a.residuals.std(), rtol=1e-12)
+
+
+def _surface_pairs(n_pairs, n_pts, seed0=10_000):
+    pairs = []
+    rng = np.random.default_rng(99)
+    for i in range(n_pairs):
+        n = n_pts if isinstance(n_pts, int) else n_pts[i]
+        Xf = O.surface(n, seed0 + 2 * i, extent=30.0)
+        x = np.concatenate((np.deg2rad(rng.uniform(-1, 1, 3)), rng.uniform(-0.2, 0.2, 3)))
+        Xm = O.transform_by_H(O.surface(n + 17 * i, seed0 + 1 + 2 * i, extent=30.0), np.linalg.inv(O.rbp_to_H(x)))
+        pairs.append((Xf, Xm))
+    return pairs
+
+
+def test_batched_engine_equals_per_pair_registration(gpu):
+    """sicp_register_batch (one launch set per stage for the whole batch, a block per pair for
+    reject + solve, per-pair stop flags) against sicp_register pair by pair: the per-pair kernels
+    are the same device code, so iteration counts, kept counts and H are IDENTICAL."""
+    pairs = _surface_pairs(9, [40_000, 25_000, 60_000, 40_000, 3_000, 40_000, 12_345, 40_000, 80_000])
+    with _capi.Engine() as e:
+        lsq = e.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
+        params = e.run_params(0.3, 1.0, 100, lsq)
+        res = e.register_batch(pairs, 1000, 10, params)
+        tm = e.timings()
+        for i, (Xf, Xm) in enumerate(pairs):
+            r = sb.register(Xf, Xm, engine=e, want_normals=False)
+            b = res[i]
+            assert b.status == 0
+            H = np.array(b.H).reshape(4, 4)
+            print(f"pair {i}: it {b.iterations} vs {r.iterations}, kept {b.n_kept} vs {r.records[-1]['n_kept']}, |dH| {np.linalg.norm(H - r.H):.2e}")
+            assert b.iterations == r.iterations and bool(b.converged) == r.converged
+            assert b.n_kept == r.records[-1]["n_kept"]
+            np.testing.assert_allclose(H, r.H, rtol=0, atol=1e-12)
+            np.testing.assert_allclose(np.array(b.x), r.rbp.get_parameter_attributes_as_list("estimated_value"), rtol=0, atol=1e-12)
+            np.testing.assert_allclose(np.array(b.sigma), r.rbp.get_parameter_attributes_as_list("estimated_uncertainty"), rtol=1e-9)
+            np.testing.assert_allclose([b.mean_res, b.std_res], [r.residuals.mean(), r.residuals.std()], rtol=1e-9, atol=1e-15)
+        # other keyword arguments travel too: observed / fixed parameters, auto weight, fewer neighbours
+        lsq2 = e.lsq_params(np.array([0.001, 0, 0, 0, 0, 0.01]), np.array([0.001, 0, 0, 0, 0, 0.01]),
+                            np.array([np.inf, 0, 0, 5.0, 0, 0]), None)
+        params2 = e.run_params(0.2, 0.5, 30, lsq2)
+        res2 = e.register_batch(pairs[:3], 700, 8, params2)
+        for i, (Xf, Xm) in enumerate(pairs[:3]):
+            r = sb.register(Xf, Xm, engine=e, want_normals=False, correspondences=700, neighbors=8, min_planarity=0.2,
+                            min_change=0.5, max_iterations=30, distance_weights=None,
+                            rbp_observed_values=(np.rad2deg(0.001), 0, 0, 0, 0, 0.01),
+                            rbp_observation_weights=(np.inf, 0, 0, 5.0, 0, 0))
+            assert res2[i].status == 0 and res2[i].iterations == r.iterations
+            np.testing.assert_allclose(np.array(res2[i].H).reshape(4, 4), r.H, rtol=0, atol=1e-12)
+            assert res2[i].x[0] == 0.001
+
+
+def test_batched_engine_per_pair_status_and_front_end(gpu):
+    """A pair without enough correspondences fails alone; simpleicp_batch reports it after the
+    gather; bad arguments are rejected for the whole call."""
+    pairs = _surface_pairs(4, 30_000)
+    t = np.sort(np.random.default_rng(1).uniform(0, 30, 5000))
+    line = np.column_stack((t, 2 * t, 3 * t))
+    pairs[2] = (line, line + 0.01)  # points on a line: planarity ~ 0 -> every correspondence rejected
+    with _capi.Engine() as e:
+        lsq = e.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
+        res = e.register_batch(pairs, 1000, 10, e.run_params(0.3, 1.0, 50, lsq))
+        assert [r.status for r in res] == [0, 0, _capi.SICP_ERR_TOO_FEW_CORR, 0]
+        with pytest.raises(_capi.SicpError, match="4096"):
+            e.register_batch(pairs, 5000, 10, e.run_params(0.3, 1.0, 50, lsq))
+    with pytest.raises(sb.batch.BatchError) as ei:
+        sb.simpleicp_batch(pairs, max_iterations=50)
+    assert ei.value.failed.tolist() == [2] and ei.value.table.shape == (4, 20)
+    table = sb.simpleicp_batch(pairs, max_iterations=50, on_error="nan")
+    assert np.isnan(table[2, :16]).all() and table[2, 16] == -_capi.SICP_ERR_TOO_FEW_CORR
+    # the batched front end equals the per-pair engines
+    pool = sb.simpleicp_batch(pairs, max_iterations=50, on_error="nan", engine="pool")
+    ok = [0, 1, 3]
+    np.testing.assert_allclose(table[ok, :16], pool[ok, :16], rtol=0, atol=1e-12)
+    assert np.array_equal(table[ok, 16:18], pool[ok, 16:18])

@@ -1,0 +1,89 @@
+"""Diagnostics (GPU), round 2: cooperative vs barrier-free reject/solve kernel on C3 and on the
+small configurations; phase stamps of the barrier-free kernel; end-to-end registrations with the
+number of iterations each path served.  Not part of the product."""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tests"))
+import simpleicp_b200 as sb
+from simpleicp_b200 import _capi
+from bench import make_pair
+
+
+def stages(e, p, reps=20):
+    out = {}
+    for fused, warm in ((0, 0), (1, 0), (1, 1)):
+        e.set_option("fused", fused)
+        e.set_option("warm_start", warm)
+        e.iterate(p, x_in=np.zeros(6), want_record=True)
+        for _ in range(12):
+            e.iterate(p, want_record=True)
+        sc = e.time_stages(p, reps, True)
+        sw = e.time_stages(p, reps, False)
+        out[(fused, warm)] = (sc, sw, e.phase_times())
+    return out
+
+
+def show(tag, res):
+    for fused, (sc, sw, t) in res.items():
+        print(f"{tag} fused={fused}: cold match {sc['match_grid']*1e3:6.1f} rs {sc['reject_solve']*1e3:6.1f} it {sc['iteration']*1e3:6.1f} us | "
+              f"warm match {sw['match_grid']*1e3:6.1f} rs {sw['reject_solve']*1e3:6.1f} it {sw['iteration']*1e3:6.1f} us | path {t[28]:.0f}")
+        if t[28] == 2:
+            print(f"    fused phases (us since block 0 entry): plan {t[10]:.1f} scan {t[11]:.1f} median {t[12]:.1f} select {t[2]:.1f} accumulate {t[3]:.1f} last-block start {t[4]:.1f} "
+                  f"partials {t[17]:.1f} assemble {t[18]:.1f} eval0 {t[21]:.1f} chol0 {t[22]:.1f} solve {t[19]:.1f} exit {t[9]:.1f} cand {t[26]:.0f}/{t[27]:.0f}")
+
+
+def c3():
+    n, K = 1_000_000, 100_000
+    X_fix, X_mov, _ = make_pair(n, 0)
+    with _capi.Engine() as e:
+        e.set_clouds(X_fix, X_mov)
+        e.set_selected(sb.pointcloud.subsample_indices(n, K).astype(np.int64))
+        e.estimate_normals(10)
+        lsq = e.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
+        p = e.run_params(0.3, 1.0, 100, lsq)
+        show("C3", stages(e, p))
+        import torch
+
+        for fused in (0, 1):
+            e.set_option("fused", fused)
+            e.set_option("warm_start", fused)
+            sb.register(X_fix, X_mov, correspondences=K, engine=e, want_normals=False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = sb.register(X_fix, X_mov, correspondences=K, engine=e, want_normals=False)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tm = e.timings()
+            print(f"C3 register fused={fused}: {dt*1e3:.2f} ms, {r.iterations} iterations, loop {r.loop_ms:.3f} ms, "
+                  f"fused {tm['fused_iterations']} re-run {tm['rerun_iterations']}")
+
+
+def small(name, kw):
+    from conftest import load_pair
+
+    X_fix, X_mov = load_pair(name)
+    with _capi.Engine() as e:
+        for fused in (0, 1):
+            e.set_option("fused", fused)
+            e.set_option("warm_start", fused)
+            sb.register(X_fix, X_mov, engine=e, want_normals=False, **kw)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                r = sb.register(X_fix, X_mov, engine=e, want_normals=False, **kw)
+            dt = (time.perf_counter() - t0) / 5
+            tm = e.timings()
+            print(f"{name} fused={fused}: {dt*1e3:.2f} ms per call, {r.iterations} iterations, loop {r.loop_ms:.3f} ms "
+                  f"({r.loop_ms/r.iterations*1e3:.1f} us/it), fused {tm['fused_iterations']} re-run {tm['rerun_iterations']}")
+
+
+if __name__ == "__main__":
+    c3()
+    small("dragon", {})
+    small("bunny", {"max_overlap_distance": 1.0})
+    small("airborne", {})
+    small("terrestrial", {})
