@@ -87,7 +87,10 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value);
  *        query in the grid search: 0 = by K, 1, 4, 8, 16), "rs_blocks" (blocks of the cooperative
  *        reject/solve kernel, 0 = one per SM), "fused" (1: iterations after the first run their
  *        reject + solve in the barrier-free kernel, 0: always the cooperative kernel),
- *        "defaults" (any value: every option back to its default)                              */
+ *        "warm_start" (1: the grid search of an iteration starts from the previous iteration's
+ *        neighbour as upper bound), "keep_knn" (see sicp_get_knn), "knn_coop" (0: one thread per
+ *        query in the k-NN search also for k <= 16), "defaults" (any value: every option back
+ *        to its default)                              */
 
 /* ---- clouds: SimpleICP.add_point_clouds (simpleicp.py:58-73) + PointCloud.X ---------------- */
 int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz /*[h|d] n_fix x 3*/, int64_t n_fix,
@@ -112,7 +115,8 @@ int32_t sicp_estimate_normals(sicp_ctx* ctx, int32_t neighbors, float* nx, float
 /* The reference's "columns already present" hook (simpleicp.py:176-178).                       */
 int32_t sicp_set_normals(sicp_ctx* ctx, const float* nx, const float* ny, const float* nz,
                          const float* planarity /*[h|d] K each*/);
-/* neighbour indices of the last sicp_estimate_normals (test/inspection hook), K x neighbors.   */
+/* neighbour indices of the last sicp_estimate_normals (test/inspection hook), K x neighbors; they
+ * are only kept when option "keep_knn" was 1 during that call.                                  */
 int32_t sicp_get_knn(sicp_ctx* ctx, int64_t* idx /*[h|d] K x k*/, double* dist2 /*[h|d] or NULL*/);
 
 /* ---- one ICP iteration, stage by stage ------------------------------------------------------ */

@@ -352,6 +352,7 @@ class Engine:
         self._check(self._lib.sicp_set_normals(self._h, *[_ptr(v) for v in a]))
 
     def get_knn(self, k: int):
+        """Neighbour lists of the last estimate_normals (needs set_option("keep_knn", 1) before it)."""
         idx = np.empty((self.K, k), dtype=np.int64)
         d2 = np.empty((self.K, k), dtype=np.float64)
         self._check(self._lib.sicp_get_knn(self._h, _ptr(idx), _ptr(d2)))

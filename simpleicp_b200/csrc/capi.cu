@@ -280,6 +280,9 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.host_sync_every = d.host_sync_every;
     c.fused = d.fused;
     c.warm_start = d.warm_start;
+    c.sphere_scan = d.sphere_scan;
+    c.keep_knn = d.keep_knn;
+    c.knn_coop = d.knn_coop;
   } else if (k == "nn_engine") {
     SICP_REQUIRE(value == 0 || value == 1 || value == 2, SICP_ERR_BAD_ARG, "nn_engine must be 0, 1 or 2");
     c.nn_engine = (int)value;
@@ -297,6 +300,12 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.grid_max_rings = (int)value;
   } else if (k == "grid_sort_cells") {
     c.grid_sort_cells = (value != 0) ? 1 : 0;
+  } else if (k == "keep_knn") {
+    c.keep_knn = (value != 0) ? 1 : 0;
+  } else if (k == "knn_coop") {
+    c.knn_coop = (value != 0) ? 1 : 0;
+  } else if (k == "sphere_scan") {
+    c.sphere_scan = (value != 0) ? 1 : 0;
   } else if (k == "warm_start") {
     c.warm_start = (value != 0) ? 1 : 0;
   } else if (k == "fused") {
@@ -456,7 +465,8 @@ int32_t sicp_set_normals(sicp_ctx* ctx, const float* nx, const float* ny, const 
 
 int32_t sicp_get_knn(sicp_ctx* ctx, int64_t* idx, double* dist2) {
   API_BEGIN(ctx)
-  SICP_REQUIRE(c.knn_k > 0 && c.have_normals, SICP_ERR_STATE, "sicp_estimate_normals has not run");
+  SICP_REQUIRE(c.knn_k > 0 && c.have_normals, SICP_ERR_STATE,
+               "no neighbour lists: set option keep_knn = 1 before sicp_estimate_normals");
   if (idx) copy_any(c, idx, c.knn_idx.p, sizeof(long long) * c.K * c.knn_k);
   if (dist2) copy_any(c, dist2, c.knn_d2.p, sizeof(double) * c.K * c.knn_k);
   sync(c);

@@ -84,6 +84,9 @@ struct Ctx {
   int knn_k = 0;
   DevBuf<long long> knn_idx;
   DevBuf<double> knn_d2;
+  DevBuf<uint32_t> knn_pos;  // K x k record positions (cooperative k-NN kernel -> PCA kernel)
+  int keep_knn = 0;          // option "keep_knn": store neighbour indices / distances for sicp_get_knn
+  int knn_coop = 1;          // option "knn_coop": 0 = the one-thread-per-query kernel also for k <= 16
 
   // per-iteration arrays
   DevBuf<long long> nn_idx;
@@ -96,6 +99,7 @@ struct Ctx {
   bool nn_pos_valid = false;         // nn_pos belongs to the current movable grid and selection
   long long nn_pos_K = 0;
   int warm_start = 1;                // option "warm_start"
+  int sphere_scan = 1;               // option "sphere_scan"
   DevBuf<double> resid;          // K, valid where keep
   DevBuf<double> resid_compact;  // kept order
   DevBuf<unsigned int> unresolved;  // query ids the grid could not bound + counter at [K]
@@ -183,6 +187,7 @@ struct Batch {
   DevBuf<long long> sel_idx, nn_idx;
   DevBuf<double> q_xyz, dist, m_xyz;
   DevBuf<float4> q_nrm;
+  DevBuf<uint32_t> knn_pos;        // n_pairs x Kmax x k
   DevBuf<unsigned int> binstore;  // n_pairs x LH_BINS x bin_cap
   int bin_cap = 0;
   DevBuf<uint32_t> nn_pos;

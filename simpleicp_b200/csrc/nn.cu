@@ -160,6 +160,7 @@ struct CorrOut {
   // result is unchanged (any point is a valid bound; ties still go to the lower index).
   uint32_t* nn_pos;
   int warm;              // nn_pos holds positions of the previous iteration
+  int sphere;            // finish a search inside the sphere of the first known point (option "sphere_scan")
 };
 __device__ __forceinline__ void store_matched(const CorrOut& co, long long qi, double x, double y, double z) {
   if (co.m_xyz) {
@@ -236,7 +237,59 @@ __device__ __forceinline__ void match_coop_body(
     const uint32_t p = co.nn_pos[qi];
     if ((long long)p < g.n_points) consider(g.recs[p], p, qx, qy, qz, best, bidx, bpos);
   }
-  for (int r = 1;; ++r) {
+  // Sphere scan: once ANY point is known (its squared distance is `best`), the nearest neighbour
+  // lies inside the sphere of that radius around the query, i.e. in the cells of the box
+  // [q - R, q + R] clipped to the grid; each x-row of the box is pruned by its distance to the
+  // query and narrowed to the chord of the sphere.  With a good bound (the previous iteration's
+  // neighbour) that is 1-4 rows of 1-2 cells instead of the 27 cells of ring 1; for a query
+  // outside the cloud's box (partial overlap) it is the small cap of the sphere that reaches into
+  // the grid instead of rings expanding through empty space.  rs = radius of the cube of cells
+  // already scanned around the query's cell (0: none).  Returns false (nothing done) when the box
+  // is too large to be worth it: the bound is poor, another ring will improve it.
+  auto sphere_scan = [&](const int rs) -> bool {
+    const double slack = 1e-9 * g.h;  // cell faces vs the floor() that assigned the points
+    const double R = sqrt(best) * (1.0 + 1e-12) + slack;
+    const int ya = cell_coord(qy - R, g.oy, g.inv_h, g.ny), yb = cell_coord(qy + R, g.oy, g.inv_h, g.ny);
+    const int za = cell_coord(qz - R, g.oz, g.inv_h, g.nz), zb = cell_coord(qz + R, g.oz, g.inv_h, g.nz);
+    const int nyb = yb - ya + 1;
+    const long long rows = (long long)nyb * (zb - za + 1);
+    if (rows > 8 * MG) return false;
+    for (int t = sub; t < (int)rows; t += MG) {
+      const int zz = za + t / nyb, yy = ya + t % nyb;
+      const double ylo = g.oy + yy * g.h, zlo = g.oz + zz * g.h;
+      const double by = fmax(fmax(ylo - qy, qy - (ylo + g.h)) - slack, 0.0);
+      const double bz = fmax(fmax(zlo - qz, qz - (zlo + g.h)) - slack, 0.0);
+      const double lb = by * by + bz * bz;
+      const double lim = best * (1.0 + 1e-12);  // strictly farther rows only: ties are still visited
+      if (lb > lim) continue;
+      const double xr = sqrt(lim - lb) * (1.0 + 1e-12) + slack;
+      const int xs = cell_coord(qx - xr, g.ox, g.inv_h, g.nx), xe = cell_coord(qx + xr, g.ox, g.inv_h, g.nx);
+      const long long row = ((long long)zz * g.ny + yy) * g.nx;
+      if (rs > 0 && abs(yy - cy) <= rs && abs(zz - cz) <= rs) {
+        // cells cx - rs .. cx + rs of this row were scanned by the rings
+        const int le = min(xe, cx - rs - 1), rb = max(xs, cx + rs + 1);
+        if (xs <= le) scan_range(g.recs, cs[row + xs], cs[row + le + 1], qx, qy, qz, best, bidx, bpos);
+        if (rb <= xe) scan_range(g.recs, cs[row + rb], cs[row + xe + 1], qx, qy, qz, best, bidx, bpos);
+      } else {
+        scan_range(g.recs, cs[row + xs], cs[row + xe + 1], qx, qy, qz, best, bidx, bpos);
+      }
+    }
+#pragma unroll
+    for (int o = MG / 2; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(gmask, best, o, MG);
+      const long long oi = __shfl_xor_sync(gmask, bidx, o, MG);
+      const uint32_t op = __shfl_xor_sync(gmask, bpos, o, MG);
+      if (od < best || (od == best && oi >= 0 && (bidx < 0 || oi < bidx))) {
+        best = od;
+        bidx = oi;
+        bpos = op;
+      }
+    }
+    return true;
+  };
+  const bool use_sphere = (cap2 < 0.0) && co.sphere;
+  if (use_sphere && best < kInf && sphere_scan(0)) resolved = true;
+  for (int r = 1; !resolved; ++r) {
     const int x0 = cx - r, x1 = cx + r;
     const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
     if (r == 1) {
@@ -354,6 +407,12 @@ __device__ __forceinline__ void match_coop_body(
       resolved = true;  // overlap filter: the side of the bound is decided (see grid_nn)
       break;
     }
+    // a point is known now: finish inside its sphere instead of growing the cube ring by ring
+    // (best is uniform across the group after the reduction, so the whole group takes one branch)
+    if (use_sphere && best < kInf && sphere_scan(r)) {
+      resolved = true;
+      break;
+    }
     if (r >= rmax) break;
   }
   if (sub != 0) return;
@@ -404,6 +463,7 @@ struct BatchMatchArgs {
   double* m_xyz;
   uint32_t* nn_pos;
   int warm;
+  int sphere;
 };
 template <int MG>
 __global__ void __launch_bounds__(128) k_match_batch(BatchMatchArgs a) {
@@ -411,7 +471,7 @@ __global__ void __launch_bounds__(128) k_match_batch(BatchMatchArgs a) {
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (gt / MG >= pd.K) return;
   const long long q = pd.q_off;
-  const CorrOut co{a.binstore + (size_t)blockIdx.y * LH_BINS * a.bin_cap, a.bin_cap, a.m_xyz + 3 * q, a.nn_pos + q, a.warm};
+  const CorrOut co{a.binstore + (size_t)blockIdx.y * LH_BINS * a.bin_cap, a.bin_cap, a.m_xyz + 3 * q, a.nn_pos + q, a.warm, a.sphere};
   match_coop_body<MG>(pd.gmov, a.state + blockIdx.y, a.q_xyz + 3 * q, a.q_nrm + q, nullptr, pd.K, 1 << 30, 1,
                       a.nn_idx + q, a.dist + q, nullptr, a.lin_hist + (size_t)blockIdx.y * (LH_BINS + 2), -1.0,
                       co, gt);
@@ -763,7 +823,7 @@ static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
   k_bf_finalize<<<(unsigned)((q_total + 127) / 128), 128, 0, c.stream>>>(
       partials, n_chunks, q_total, qlist, qcount, c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p,
       with_distance ? 1 : 0, c.nn_idx.p, out, with_distance ? c.lin_hist.p : nullptr,
-      with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, nullptr, 0} : CorrOut{nullptr, 0, nullptr, nullptr, 0});
+      with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, nullptr, 0, 0} : CorrOut{nullptr, 0, nullptr, nullptr, 0, 0});
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 2;
 }
@@ -815,6 +875,7 @@ void batch_match_launch(Ctx& c, Batch& b, bool warm) {
   a.m_xyz = b.m_xyz.p;
   a.nn_pos = b.nn_pos.p;
   a.warm = warm ? 1 : 0;
+  a.sphere = c.sphere_scan;
   // lanes per query as in the single-pair launch, by the number of queries in flight
   const long long total = b.Kmax * b.n_pairs;
   int mg = c.match_group;
@@ -844,8 +905,8 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   c.m_xyz.reserve(3 * std::max<long long>(K, 1));
   c.nn_pos.reserve(std::max<long long>(K, 1));
   const bool warm = with_distance && c.warm_start && c.nn_pos_valid && c.nn_pos_K == K;
-  const CorrOut co = with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, c.nn_pos.p, warm ? 1 : 0}
-                                   : CorrOut{nullptr, 0, nullptr, nullptr, 0};
+  const CorrOut co = with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, c.nn_pos.p, warm ? 1 : 0, c.sphere_scan}
+                                   : CorrOut{nullptr, 0, nullptr, nullptr, 0, 0};
   if (with_distance) {
     c.nn_pos_valid = (c.nn_engine != SICP_NN_BRUTE) && c.match_group != 1;
     c.nn_pos_K = K;

@@ -169,6 +169,273 @@ __device__ __forceinline__ void knn_pca_body(const GridView& g, const double* __
   q_nrm[i] = o;
 }
 
+// =============================================================================================
+// Cooperative k-NN for k <= 16 (the reference's default is 10): MG lanes share one query.
+//   * every lane scans its share of the grid rows (x-contiguous cell runs) and keeps its OWN best
+//     KC candidates (distance, record position) in registers — a fully unrolled compare-exchange
+//     insertion, no dynamically indexed array, hence no local-memory stack frame (the
+//     one-thread-per-query kernel above carries a 1.3 KB frame for its 64-slot list);
+//   * after each ring the group extracts the k-th smallest of the union of its lists (k rounds of
+//     a shuffle arg-min over the list heads): that is the exact current k-th neighbour distance,
+//     used to prune rows of the next ring and for the termination proof
+//     (k-th best <= distance to every unexplored cell);
+//   * the final k rounds emit the neighbours in (distance, index) order as record positions.
+// The covariance / eigen-solve run in a second kernel, one thread per query (k_pca_from_knn): in
+// this one three of four lanes would idle through the ~2000-instruction dgeev walk.  It reads
+// the neighbours from the cell-sorted records the search just touched (L2-hot), not from the
+// caller-order cloud.  Ordering (distance, then original index) and the summation order of mean
+// and covariance are those of the kernel above: the float32 normals are bit-identical.
+// =============================================================================================
+template <int KC>
+struct LaneList {
+  double d[KC];
+  uint32_t p[KC];
+};
+
+// (da, pa) before (db, pb)?  Equal distances are ordered by ORIGINAL index (deterministic; the
+// position inside a cell depends on the order of the build's atomics); that needs the records,
+// but only on an exact tie.
+__device__ __forceinline__ bool cand_less(const Rec* __restrict__ recs, double da, uint32_t pa, double db,
+                                          uint32_t pb) {
+  if (da != db) return da < db;
+  if (pb == 0xffffffffu) return pa != 0xffffffffu;
+  if (pa == 0xffffffffu) return false;
+  return recs[pa].idx < recs[pb].idx;
+}
+
+template <int KC>
+__device__ __forceinline__ void lane_insert(const Rec* __restrict__ recs, LaneList<KC>& L, double d, uint32_t p) {
+  if (!cand_less(recs, d, p, L.d[KC - 1], L.p[KC - 1])) return;
+  L.d[KC - 1] = d;
+  L.p[KC - 1] = p;
+#pragma unroll
+  for (int j = KC - 1; j >= 1; --j) {
+    const bool sw = cand_less(recs, L.d[j], L.p[j], L.d[j - 1], L.p[j - 1]);
+    const double td = sw ? L.d[j - 1] : L.d[j];
+    const uint32_t tp = sw ? L.p[j - 1] : L.p[j];
+    L.d[j - 1] = sw ? L.d[j] : L.d[j - 1];
+    L.p[j - 1] = sw ? L.p[j] : L.p[j - 1];
+    L.d[j] = td;
+    L.p[j] = tp;
+  }
+}
+
+template <int KC>
+__device__ __forceinline__ void scan_range_l(const Rec* __restrict__ recs, uint32_t s, uint32_t e, double qx,
+                                             double qy, double qz, double bound, LaneList<KC>& L) {
+  for (uint32_t i = s; i < e; i += 4) {
+    const uint32_t last = e - 1;
+    const uint32_t i1 = min(i + 1, last), i2 = min(i + 2, last), i3 = min(i + 3, last);
+    const Rec r0 = recs[i];
+    const Rec r1 = recs[i1];
+    const Rec r2 = recs[i2];
+    const Rec r3 = recs[i3];
+    const Rec* rr[4] = {&r0, &r1, &r2, &r3};
+    const uint32_t ii[4] = {i, i1, i2, i3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j == 0 || ii[j] != ii[j - 1]) {  // the clamped tail repeats the last record: skip repeats
+        const double dx = rr[j]->x - qx, dy = rr[j]->y - qy, dz = rr[j]->z - qz;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 <= bound) lane_insert<KC>(recs, L, d2, ii[j]);
+      }
+    }
+  }
+}
+
+// k rounds of arg-min over the heads of the lanes' sorted lists.  Returns the k-th smallest of
+// the union (kInf if the union holds fewer than k); when out != nullptr lane 0 of the group
+// stores the positions in order.
+template <int MG, int KC>
+__device__ __forceinline__ double union_kth(const Rec* __restrict__ recs, const LaneList<KC>& L, int k,
+                                            unsigned int gmask, int sub, uint32_t* __restrict__ out) {
+  int head = 0;
+  double last = kInf;
+  for (int round = 0; round < k; ++round) {
+    double d = kInf;
+    uint32_t p = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < KC; ++j)
+      if (j == head) {
+        d = L.d[j];
+        p = L.p[j];
+      }
+    double bd = d;
+    uint32_t bp = p;
+    int bl = sub;
+#pragma unroll
+    for (int o = MG / 2; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(gmask, bd, o, MG);
+      const uint32_t op = __shfl_xor_sync(gmask, bp, o, MG);
+      const int ol = __shfl_xor_sync(gmask, bl, o, MG);
+      // identical (d, p) cannot come from two lanes (a record is scanned by one lane only)
+      const bool take = cand_less(recs, od, op, bd, bp);
+      if (take) {
+        bd = od;
+        bp = op;
+        bl = ol;
+      }
+    }
+    if (bl == sub && bp != 0xffffffffu) ++head;
+    last = (bp == 0xffffffffu) ? kInf : bd;
+    if (out != nullptr && sub == 0) out[round] = bp;
+  }
+  return last;
+}
+
+template <int MG, int KC>
+__device__ __forceinline__ void knn_coop_body(const GridView& g, const double* __restrict__ q_xyz, long long K,
+                                              int k, uint32_t* __restrict__ knn_pos, const long long gt) {
+  const long long qi = gt / MG;
+  const int sub = threadIdx.x & (MG - 1);
+  if (qi >= K) return;  // a whole group leaves together
+  const unsigned int gmask = (MG == 32) ? 0xffffffffu : (((1u << MG) - 1u) << ((threadIdx.x & 31) & ~(MG - 1)));
+  const double qx = q_xyz[3 * qi + 0], qy = q_xyz[3 * qi + 1], qz = q_xyz[3 * qi + 2];
+  const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+  const uint32_t* __restrict__ cs = g.cell_start;
+  LaneList<KC> L;
+#pragma unroll
+  for (int j = 0; j < KC; ++j) {
+    L.d[j] = kInf;
+    L.p[j] = 0xffffffffu;
+  }
+  double B = kInf;  // current k-th best of the union (upper bound of the final one)
+  for (int r = 1;; ++r) {
+    const int x0 = cx - r, x1 = cx + r;
+    const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
+    const int side = 2 * r + 1, items = side * side;
+    const double lim = B * (1.0 + 1e-12);  // strictly farther rows only: ties are still visited
+    int dzr = sub / side, dyr = sub - dzr * side;
+    for (int t = sub; t < items; t += MG, dyr += MG) {
+      while (dyr >= side) {
+        dyr -= side;
+        ++dzr;
+      }
+      const int dz = dzr - r, dy = dyr - r;
+      const int y = cy + dy, z = cz + dz;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      const bool full = (r == 1) || dy == -r || dy == r || dz == -r || dz == r;
+      if (r > 1) {
+        const double by = (dy < 0) ? qy - (g.oy + (y + 1) * g.h) : ((dy > 0) ? (g.oy + y * g.h) - qy : 0.0);
+        const double bz = (dz < 0) ? qz - (g.oz + (z + 1) * g.h) : ((dz > 0) ? (g.oz + z * g.h) - qz : 0.0);
+        const double lb = fmax(by, 0.0) * fmax(by, 0.0) + fmax(bz, 0.0) * fmax(bz, 0.0);
+        if (lb > lim) continue;
+      }
+      const long long row = ((long long)z * g.ny + y) * g.nx;
+      if (full) {
+        scan_range_l<KC>(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, lim, L);
+      } else {
+        if (x0 >= 0) scan_range_l<KC>(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, lim, L);
+        if (x1 < g.nx) scan_range_l<KC>(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, lim, L);
+      }
+    }
+    B = union_kth<MG, KC>(g.recs, L, k, gmask, sub, nullptr);
+    const int y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
+    double guard = kInf;
+    if (x0 > 0) guard = fmin(guard, qx - (g.ox + x0 * g.h));
+    if (x1 < g.nx - 1) guard = fmin(guard, (g.ox + (x1 + 1) * g.h) - qx);
+    if (y0 > 0) guard = fmin(guard, qy - (g.oy + y0 * g.h));
+    if (y1 < g.ny - 1) guard = fmin(guard, (g.oy + (y1 + 1) * g.h) - qy);
+    if (z0 > 0) guard = fmin(guard, qz - (g.oz + z0 * g.h));
+    if (z1 < g.nz - 1) guard = fmin(guard, (g.oz + (z1 + 1) * g.h) - qz);
+    if (guard >= kInf) break;  // the block covers the whole grid
+    guard -= 1e-9 * g.h;
+    if (B < kInf && guard > 0.0 && B <= guard * guard) break;
+  }
+  union_kth<MG, KC>(g.recs, L, k, gmask, sub, knn_pos + qi * k);
+}
+
+template <int MG, int KC>
+__global__ void __launch_bounds__(128)
+    k_knn_coop(GridView g, const double* __restrict__ q_xyz, long long K, int k, uint32_t* __restrict__ knn_pos) {
+  knn_coop_body<MG, KC>(g, q_xyz, K, k, knn_pos, blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+
+// covariance (np.cov, ddof = 1) + eigen-solve + float32 store from the neighbour positions; the
+// arithmetic of knn_pca_body, the points taken from the cell-sorted records
+__device__ __forceinline__ void pca_from_knn_body(const GridView& g, const double* __restrict__ q_xyz, long long K,
+                                                  int k, int sign_mode, const uint32_t* __restrict__ knn_pos,
+                                                  float4* __restrict__ q_nrm, long long* __restrict__ knn_idx,
+                                                  double* __restrict__ knn_d2, const long long i) {
+  if (i >= K) return;
+  const uint32_t* __restrict__ pp = knn_pos + i * k;
+  int n = 0;
+  double mx = 0, my = 0, mz = 0;
+  for (int j = 0; j < k; ++j) {
+    const uint32_t p = pp[j];
+    if (p == 0xffffffffu) break;
+    const Rec r = g.recs[p];
+    mx += r.x;
+    my += r.y;
+    mz += r.z;
+    ++n;
+    if (knn_idx) {
+      knn_idx[i * k + j] = r.idx;
+      if (knn_d2) {
+        const double dx = r.x - q_xyz[3 * i + 0], dy = r.y - q_xyz[3 * i + 1], dz = r.z - q_xyz[3 * i + 2];
+        knn_d2[i * k + j] = dx * dx + dy * dy + dz * dz;
+      }
+    }
+  }
+  const double inv = 1.0 / (double)n;
+  mx *= inv;
+  my *= inv;
+  mz *= inv;
+  double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+  for (int j = 0; j < n; ++j) {
+    const Rec r = g.recs[pp[j]];
+    const double dx = r.x - mx, dy = r.y - my, dz = r.z - mz;
+    c00 = fma(dx, dx, c00);
+    c01 = fma(dx, dy, c01);
+    c02 = fma(dx, dz, c02);
+    c11 = fma(dy, dy, c11);
+    c12 = fma(dy, dz, c12);
+    c22 = fma(dz, dz, c22);
+  }
+  const double f = 1.0 / (double)(n - 1);
+  c00 *= f;
+  c01 *= f;
+  c02 *= f;
+  c11 *= f;
+  c12 *= f;
+  c22 *= f;
+  double w[3], nn[3];
+  eig3_smallest(c00, c01, c02, c11, c12, c22, sign_mode, w, nn);
+  float4 o;
+  o.x = (float)nn[0];
+  o.y = (float)nn[1];
+  o.z = (float)nn[2];
+  o.w = (float)((w[1] - w[2]) / w[0]);
+  q_nrm[i] = o;
+}
+
+__global__ void __launch_bounds__(128)
+    k_pca_from_knn(GridView g, const double* __restrict__ q_xyz, long long K, int k, int sign_mode,
+                   const uint32_t* __restrict__ knn_pos, float4* __restrict__ q_nrm,
+                   long long* __restrict__ knn_idx, double* __restrict__ knn_d2) {
+  pca_from_knn_body(g, q_xyz, K, k, sign_mode, knn_pos, q_nrm, knn_idx, knn_d2,
+                    blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+
+// batched forms: blockIdx.y = pair
+template <int MG, int KC>
+__global__ void __launch_bounds__(128)
+    k_knn_coop_batch(const PairDev* __restrict__ pairs, const double* __restrict__ q_xyz, int k, long long Kmax,
+                     uint32_t* __restrict__ knn_pos) {
+  const PairDev pd = pairs[blockIdx.y];
+  knn_coop_body<MG, KC>(pd.gfix, q_xyz + 3 * pd.q_off, pd.K, k, knn_pos + (size_t)blockIdx.y * Kmax * k,
+                        blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128)
+    k_pca_from_knn_batch(const PairDev* __restrict__ pairs, const double* __restrict__ q_xyz, int k, long long Kmax,
+                         int sign_mode, const uint32_t* __restrict__ knn_pos, float4* __restrict__ q_nrm) {
+  const PairDev pd = pairs[blockIdx.y];
+  pca_from_knn_body(pd.gfix, q_xyz + 3 * pd.q_off, pd.K, k, sign_mode, knn_pos + (size_t)blockIdx.y * Kmax * k,
+                    q_nrm + pd.q_off, nullptr, nullptr, blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+
 __global__ void __launch_bounds__(128)
     k_knn_pca(GridView g, const double* __restrict__ fix_xyz, const double* __restrict__ q_xyz,
               long long K, int k, int sign_mode, float4* __restrict__ q_nrm,
@@ -194,12 +461,37 @@ void estimate_normals_launch(Ctx& c, int k) {
   SICP_REQUIRE((long long)k <= c.n_fix, SICP_ERR_BAD_ARG,
                "neighbors exceeds the number of points in the fixed cloud");
   c.q_nrm.reserve(std::max<long long>(c.K, 1));
-  c.knn_idx.reserve((size_t)c.K * k);
-  c.knn_d2.reserve((size_t)c.K * k);
-  c.knn_k = k;
+  // the neighbour lists leave the SM only when somebody wants to look at them (option "keep_knn")
+  long long* kidx = nullptr;
+  double* kd2 = nullptr;
+  if (c.keep_knn) {
+    c.knn_idx.reserve((size_t)c.K * k);
+    c.knn_d2.reserve((size_t)c.K * k);
+    kidx = c.knn_idx.p;
+    kd2 = c.knn_d2.p;
+  }
+  c.knn_k = c.keep_knn ? k : 0;
+  if (k <= 16 && c.knn_coop) {
+    c.knn_pos.reserve((size_t)c.K * k);
+    // lanes per query: 8 while there are few queries (latency-bound), 4 once they fill the machine
+    const int mg = (c.K <= 32768) ? 8 : 4;
+    const unsigned blocks = (unsigned)((c.K * mg + 127) / 128);
+    const GridView g = c.gfix.view();
+    if (mg == 8) {
+      if (k <= 12) k_knn_coop<8, 12><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
+      else k_knn_coop<8, 16><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
+    } else {
+      if (k <= 12) k_knn_coop<4, 12><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
+      else k_knn_coop<4, 16><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
+    }
+    k_pca_from_knn<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.sign_mode,
+                                                                        c.knn_pos.p, c.q_nrm.p, kidx, kd2);
+    SICP_CUDA(cudaGetLastError());
+    c.tm.kernel_launches += 2;
+    return;
+  }
   k_knn_pca<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(
-      c.gfix.view(), c.fix_xyz.p, c.q_xyz.p, c.K, k, c.sign_mode, c.q_nrm.p, c.knn_idx.p,
-      c.knn_d2.p);
+      c.gfix.view(), c.fix_xyz.p, c.q_xyz.p, c.K, k, c.sign_mode, c.q_nrm.p, kidx, kd2);
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 1;
 }
@@ -207,6 +499,24 @@ void estimate_normals_launch(Ctx& c, int k) {
 void batch_normals_launch(Ctx& c, Batch& b, int k) {
   SICP_REQUIRE(k >= 2 && k <= kMaxK, SICP_ERR_BAD_ARG,
                "neighbors must be between 2 and 64 (got " + std::to_string(k) + ")");
+  if (k <= 16 && c.knn_coop) {
+    b.knn_pos.reserve((size_t)b.n_pairs * b.Kmax * k);
+    const long long total = b.Kmax * b.n_pairs;
+    const int mg = (total <= 32768) ? 8 : 4;
+    const dim3 grid((unsigned)((b.Kmax * mg + 127) / 128), b.n_pairs);
+    if (mg == 8) {
+      if (k <= 12) k_knn_coop_batch<8, 12><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
+      else k_knn_coop_batch<8, 16><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
+    } else {
+      if (k <= 12) k_knn_coop_batch<4, 12><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
+      else k_knn_coop_batch<4, 16><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
+    }
+    k_pca_from_knn_batch<<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
+        b.pairs.p, b.q_xyz.p, k, b.Kmax, c.sign_mode, b.knn_pos.p, b.q_nrm.p);
+    SICP_CUDA(cudaGetLastError());
+    c.tm.kernel_launches += 2;
+    return;
+  }
   k_knn_pca_batch<<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
       b.pairs.p, b.fix_xyz.p, b.q_xyz.p, k, c.sign_mode, b.q_nrm.p);
   SICP_CUDA(cudaGetLastError());

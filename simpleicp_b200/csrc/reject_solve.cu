@@ -269,7 +269,7 @@ __device__ __noinline__ void block_select(Shared& s, const unsigned long long* k
 // |d - center|.  Result broadcast through s.bc[0] (lower middle) and s.bc[1] (upper middle).
 template <bool MULTI, int SEL>
 __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double center,
-                             unsigned int& n1_out) {
+                             unsigned int& n1_out, const int bid = blockIdx.x, const int G = gridDim.x) {
   const long long K = a.K;
   const double minpl = a.stat_minpl;
   unsigned int* ghist_base = wk.hist + (size_t)SEL * RS_LEVELS * RS_BINS;
@@ -282,8 +282,8 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     const int n_bins = 1 << width;
     for (int b = threadIdx.x; b < RS_BINS; b += RS_THREADS) s.hist[b] = 0;
     __syncthreads();
-    for (long long i = blockIdx.x * (long long)RS_THREADS + threadIdx.x; i < K;
-         i += (long long)gridDim.x * RS_THREADS) {
+    for (long long i = bid * (long long)RS_THREADS + threadIdx.x; i < K;
+         i += (long long)G * RS_THREADS) {
       if ((double)a.q_nrm[i].w >= minpl) {
         const double v = (SEL == 0) ? a.dist[i] : fabs(a.dist[i] - center);
         const unsigned long long key = f64_to_key(v);
@@ -318,7 +318,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     __syncthreads();
     if (cnt <= RS_CAP - 2 || level == RS_LEVELS - 1) break;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (bid == 0 && threadIdx.x == 0) {
     wk.phase_t[10 + SEL * 4] = global_timer_ns();
     wk.phase_t[24 + SEL] = (unsigned long long)(level + 1);
     wk.phase_t[26 + SEL] = (unsigned long long)cnt;
@@ -334,8 +334,8 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     if (threadIdx.x == 0) s.total = 0;
     __syncthreads();
   }
-  for (long long i = blockIdx.x * (long long)RS_THREADS + threadIdx.x; i < K;
-       i += (long long)gridDim.x * RS_THREADS) {
+  for (long long i = bid * (long long)RS_THREADS + threadIdx.x; i < K;
+       i += (long long)G * RS_THREADS) {
     if ((double)a.q_nrm[i].w >= minpl) {
       const double v = (SEL == 0) ? a.dist[i] : fabs(a.dist[i] - center);
       const unsigned long long key = f64_to_key(v);
@@ -367,7 +367,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     }
   }
   gsync<MULTI>(wk.barrier);
-  if (blockIdx.x == 0 && threadIdx.x == 0) wk.phase_t[11 + SEL * 4] = global_timer_ns();
+  if (bid == 0 && threadIdx.x == 0) wk.phase_t[11 + SEL * 4] = global_timer_ns();
   const unsigned long long above = MULTI ? *gmin : wmin[0];
   unsigned long long klo, khi;
   if (gather) {
@@ -382,7 +382,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     khi = (k + 1 < cnt) ? prefix : above;
   }
   __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x == 0) wk.phase_t[12 + SEL * 4] = global_timer_ns();
+  if (bid == 0 && threadIdx.x == 0) wk.phase_t[12 + SEL * 4] = global_timer_ns();
   if (threadIdx.x == 0) {
     s.bc[0] = key_to_f64(klo);
     s.bc[1] = even ? key_to_f64(khi) : key_to_f64(klo);
@@ -1339,16 +1339,28 @@ struct SharedF {
 // the candidates come from a handful of adjacent histogram bins).
 __device__ __forceinline__ void rank_select(Shared& s, const unsigned long long* keys, int n, unsigned int k,
                                             unsigned long long& klo, unsigned long long& khi) {
+  // RS_THREADS / n threads share one candidate (each compares it with a slice of the list)
   const int tid = threadIdx.x;
-  if (tid < n) {
-    const unsigned long long key = keys[tid];
-    unsigned int r = 0;
-    for (int j = 0; j < n; ++j) {
+  const int parts = max(1, min(RS_THREADS / max(n, 1), 8));
+  const int c = tid / parts, part = tid - c * parts;
+  if (tid < 256) s.h256[tid] = 0;
+  // (parts > 1 implies n <= RS_THREADS / 2 = 192 < 256 slots)
+  __syncthreads();
+  unsigned int r = 0;
+  unsigned long long key = 0;
+  if (c < n) {
+    key = keys[c];
+    for (int j = part; j < n; j += parts) {
       const unsigned long long kj = keys[j];
-      r += (kj < key || (kj == key && j < tid)) ? 1u : 0u;
+      r += (kj < key || (kj == key && j < c)) ? 1u : 0u;
     }
-    if (r == k) s.small[0] = key;
-    if (r == k + 1u) s.small[1] = key;
+    if (parts > 1) atomicAdd(&s.h256[c], r);
+  }
+  __syncthreads();
+  if (c < n && part == 0) {
+    const unsigned int rank = (parts > 1) ? s.h256[c] : r;
+    if (rank == k) s.small[0] = key;
+    if (rank == k + 1u) s.small[1] = key;
   }
   __syncthreads();
   klo = s.small[0];
@@ -1370,6 +1382,8 @@ __device__ bool fused_select(SharedF& sf, const RSArgs& a, RSWork wk, const DevS
     v[j] = (b < LH_BINS) ? __ldcg(&wk.lin_hist[b]) : 0u;
     sum += v[j];
   }
+  // (requested together with the bins: one round trip, not two)
+  const unsigned int under = __ldcg(&wk.lin_hist[LH_BINS]), over = __ldcg(&wk.lin_hist[LH_BINS + 1]);
   unsigned int incl = sum;
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -1398,7 +1412,6 @@ __device__ bool fused_select(SharedF& sf, const RSArgs& a, RSWork wk, const DevS
   }
   __syncthreads();
   const unsigned int* P = s.hist;
-  const unsigned int under = __ldcg(&wk.lin_hist[LH_BINS]), over = __ldcg(&wk.lin_hist[LH_BINS + 1]);
   const unsigned int n1 = under + total_in + over;
   n1_out = n1;
   if (n1 == 0) return true;
@@ -1536,12 +1549,12 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
     // a single block owns the whole problem (K <= 4096, or one pair of a batch): no prediction —
     // first iteration, large change — simply means the radix selection, here and now
     __syncthreads();
-    radix_median<false, 0>(s, a, wk, 0.0, n1);
+    radix_median<false, 0>(s, a, wk, 0.0, n1, 0, 1);
     if (n1 != 0) {
       median = a.variant ? s.bc[1] : 0.5 * (s.bc[0] + s.bc[1]);
       __syncthreads();
       unsigned int n1b = 0;
-      radix_median<false, 1>(s, a, wk, median, n1b);
+      radix_median<false, 1>(s, a, wk, median, n1b, 0, 1);
       mad = a.variant ? s.bc[1] : 0.5 * (s.bc[0] + s.bc[1]);
     }
     __syncthreads();
@@ -1650,6 +1663,9 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
   __syncthreads();
   if (!sf.is_last) return;
   __threadfence();
+  // state the serial tail needs: requested now, so that the round trips overlap the partial sums
+  const double prev_mean = __ldcg(&st->prev_mean), prev_std = __ldcg(&st->prev_std), w_state = __ldcg(&st->w);
+  const unsigned int n_bf = a.unresolved ? __ldcg(&a.unresolved[K]) : 0u;
   if (tid == 0) {
     *wk.ticket = 0u;
     wk.phase_t[4] = global_timer_ns();
@@ -1728,7 +1744,7 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
   const double mean_d = (n_kept > 0) ? sum_d / (double)n_kept : nan("");
   const double var_d = (n_kept > 0) ? fmax(sum_d2 / (double)n_kept - mean_d * mean_d, 0.0) : nan("");
   const double var_d1 = (n_kept > 1) ? fmax(sum_d2 - (double)n_kept * mean_d * mean_d, 0.0) / (double)(n_kept - 1) : nan("");
-  double w = st->w;
+  double w = w_state;
   if (a.variant) {
     w = 1.0;
   } else if (a.it == 0 || !(w > 0.0)) {
@@ -1763,7 +1779,7 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
     rec->std_dist = sqrt(a.variant ? var_d1 : var_d);
     rec->distance_weight = w;
     rec->lm_iterations = lo.iters;
-    rec->n_bruteforce = a.unresolved ? (int)a.unresolved[K] : 0;
+    rec->n_bruteforce = (int)n_bf;
     st->n_kept = n_kept;
     st->skip = skip;
     st->w = w;
@@ -1802,7 +1818,7 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
                               : sqrt(fmax(sum_r2 / n - mean * mean, 0.0));
   int stop = 0;
   if (a.it > 0) {
-    const double m0 = st->prev_mean, s0 = st->prev_std;
+    const double m0 = prev_mean, s0 = prev_std;
     const double cmn = (m0 == 0.0) ? ((mean == 0.0) ? 0.0 : kInf) : fabs((mean - m0) / m0 * 100.0);
     const double csd = (s0 == 0.0) ? ((sd == 0.0) ? 0.0 : kInf) : fabs((sd - s0) / s0 * 100.0);
     stop = (cmn < a.min_change && csd < a.min_change) ? 1 : 0;

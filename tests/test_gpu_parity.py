@@ -188,6 +188,7 @@ def test_normals(gpu, name, k):
     X_fix, X_mov = load_pair(name)
     with _capi.Engine() as e:
         e.set_option("sign_mode", _capi.SIGN_CANONICAL)
+        e.set_option("keep_knn", 1)
         e.set_clouds(X_fix, X_mov)
         e.set_selected(g["idx_sel"])
         nx, ny, nz, pl = e.estimate_normals(k)

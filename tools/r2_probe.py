@@ -16,9 +16,10 @@ from bench import make_pair
 
 def stages(e, p, reps=20):
     out = {}
-    for fused, warm in ((0, 0), (1, 0), (1, 1)):
+    for fused, warm in ((0, 0), (1, 1), (1, 2)):
         e.set_option("fused", fused)
-        e.set_option("warm_start", warm)
+        e.set_option("warm_start", 1 if warm else 0)
+        e.set_option("sphere_scan", 1 if warm == 2 else 0)
         e.iterate(p, x_in=np.zeros(6), want_record=True)
         for _ in range(12):
             e.iterate(p, want_record=True)
@@ -52,6 +53,7 @@ def c3():
         for fused in (0, 1):
             e.set_option("fused", fused)
             e.set_option("warm_start", fused)
+            e.set_option("sphere_scan", fused)
             sb.register(X_fix, X_mov, correspondences=K, engine=e, want_normals=False)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -60,7 +62,20 @@ def c3():
             dt = time.perf_counter() - t0
             tm = e.timings()
             print(f"C3 register fused={fused}: {dt*1e3:.2f} ms, {r.iterations} iterations, loop {r.loop_ms:.3f} ms, "
-                  f"fused {tm['fused_iterations']} re-run {tm['rerun_iterations']}")
+                  f"fused {tm['fused_iterations']} re-run {tm['rerun_iterations']}, normals {tm['normals_ms']:.3f} ms, "
+                  f"grids {tm['grid_fix_ms']:.3f}+{tm['grid_mov_ms']:.3f} ms")
+        # first iteration (far queries) with and without the sphere scan
+        lsq = e.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
+        p = e.run_params(0.3, 1.0, 100, lsq)
+        for sph in (0, 1):
+            e.set_option("sphere_scan", sph)
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                rec = e.iterate(p, x_in=np.zeros(6), want_record=True)
+                ts.append((time.perf_counter() - t0) * 1e6)
+            print(f"C3 first iteration (host wall, incl. sync) sphere_scan={sph}: {min(ts):.0f} us, brute-force queries {rec.n_bruteforce}")
 
 
 def small(name, kw):
@@ -71,6 +86,7 @@ def small(name, kw):
         for fused in (0, 1):
             e.set_option("fused", fused)
             e.set_option("warm_start", fused)
+            e.set_option("sphere_scan", fused)
             sb.register(X_fix, X_mov, engine=e, want_normals=False, **kw)
             t0 = time.perf_counter()
             for _ in range(5):
