@@ -88,8 +88,8 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value);
  *        reject/solve kernel, 0 = one per SM), "fused" (1: iterations after the first run their
  *        reject + solve in the barrier-free kernel, 0: always the cooperative kernel),
  *        "warm_start" (1: the grid search of an iteration starts from the previous iteration's
- *        neighbour as upper bound), "keep_knn" (see sicp_get_knn), "knn_coop" (0: one thread per
- *        query in the k-NN search also for k <= 16), "defaults" (any value: every option back
+ *        neighbour as upper bound), "keep_knn" (see sicp_get_knn), "knn_coop" (k-NN search: 1 cooperative
+ *        lanes per query (k <= 16), 0 one thread per query, -1 (default) by the number of queries), "defaults" (any value: every option back
  *        to its default)                              */
 
 /* ---- clouds: SimpleICP.add_point_clouds (simpleicp.py:58-73) + PointCloud.X ---------------- */

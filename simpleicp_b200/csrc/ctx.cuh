@@ -86,7 +86,7 @@ struct Ctx {
   DevBuf<double> knn_d2;
   DevBuf<uint32_t> knn_pos;  // K x k record positions (cooperative k-NN kernel -> PCA kernel)
   int keep_knn = 0;          // option "keep_knn": store neighbour indices / distances for sicp_get_knn
-  int knn_coop = 1;          // option "knn_coop": 0 = the one-thread-per-query kernel also for k <= 16
+  int knn_coop = -1;         // option "knn_coop": 1 cooperative lanes (k <= 16), 0 one thread per query, -1 by K
 
   // per-iteration arrays
   DevBuf<long long> nn_idx;

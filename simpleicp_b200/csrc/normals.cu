@@ -4,9 +4,11 @@
 // the smallest eigenvalue, planarity = (l_mid - l_min) / l_max, both rounded to float32 exactly
 // where the reference does (pointcloud.py:180-183, 194-198).
 //
-// Fused: grid k-NN (float64, sorted top-k, exact ring expansion) -> covariance -> eigen-solve
-// -> float4 (nx, ny, nz, planarity) store; the neighbour lists never leave the SM unless the
-// caller asks for them.
+// Two kernels: an exact grid k-NN (float64, ring expansion until the k-th best is provably final)
+// that emits the neighbours as positions in the cell-sorted record array, and the covariance /
+// eigen-solve / float4 (nx, ny, nz, planarity) store, which reads those records (L2-hot) instead
+// of gathering the caller-order cloud.  Neighbour indices and distances are written out only
+// when the caller asked for them (option "keep_knn").
 #include <algorithm>
 
 #include "ctx.cuh"
@@ -17,157 +19,6 @@ namespace sicp {
 namespace {
 
 constexpr int kMaxK = 64;
-
-struct TopK {
-  double d2[kMaxK];
-  long long idx[kMaxK];
-  int n;
-  int k;
-  __device__ __forceinline__ bool full() const { return n == k; }
-  __device__ __forceinline__ double worst() const { return d2[n - 1]; }
-  __device__ __forceinline__ void consider(double d, long long i) {
-    if (n == k) {
-      if (!(d < d2[k - 1] || (d == d2[k - 1] && i < idx[k - 1]))) return;
-    } else {
-      ++n;
-    }
-    int j = n - 1;
-    while (j > 0 && (d2[j - 1] > d || (d2[j - 1] == d && idx[j - 1] > i))) {
-      d2[j] = d2[j - 1];
-      idx[j] = idx[j - 1];
-      --j;
-    }
-    d2[j] = d;
-    idx[j] = i;
-  }
-};
-
-// four 32-byte records in flight per step (the search is latency-bound); the tail re-reads the
-// last record, which the (distance, index) ordering of the top-k list ignores as a duplicate
-__device__ __forceinline__ void scan_range_k(const Rec* __restrict__ recs, uint32_t s, uint32_t e,
-                                             double qx, double qy, double qz, TopK& tk) {
-  for (uint32_t i = s; i < e; i += 4) {
-    const uint32_t last = e - 1;
-    const Rec r0 = recs[i];
-    const Rec r1 = recs[min(i + 1, last)];
-    const Rec r2 = recs[min(i + 2, last)];
-    const Rec r3 = recs[min(i + 3, last)];
-    const int n = (int)min(4u, e - i);
-    const Rec* rr[4] = {&r0, &r1, &r2, &r3};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j < n) {
-        const double dx = rr[j]->x - qx, dy = rr[j]->y - qy, dz = rr[j]->z - qz;
-        tk.consider(dx * dx + dy * dy + dz * dz, rr[j]->idx);
-      }
-    }
-  }
-}
-
-// Exact k-NN by ring expansion.  Rows (x-contiguous cell runs) whose distance bound already
-// exceeds the current k-th best are skipped; ring 1 starts with the query's own row so that the
-// list fills with near points first.
-__device__ void grid_knn(const GridView& g, double qx, double qy, double qz, TopK& tk) {
-  const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
-  const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
-  const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
-  const uint32_t* __restrict__ cs = g.cell_start;
-  for (int r = 1;; ++r) {
-    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
-    const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
-    const int side = 2 * r + 1, items = side * side, centre = items / 2;
-    for (int t0 = 0; t0 < items; ++t0) {
-      // visit the centre row first in ring 1, then the others in order
-      const int t = (r == 1) ? ((t0 == 0) ? centre : ((t0 <= centre) ? t0 - 1 : t0)) : t0;
-      const int dz = t / side - r, dy = t % side - r;
-      const int y = cy + dy, z = cz + dz;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      if (tk.full()) {
-        const double by = (dy < 0) ? qy - (g.oy + (y + 1) * g.h) : ((dy > 0) ? (g.oy + y * g.h) - qy : 0.0);
-        const double bz = (dz < 0) ? qz - (g.oz + (z + 1) * g.h) : ((dz > 0) ? (g.oz + z * g.h) - qz : 0.0);
-        const double lb = fmax(by, 0.0) * fmax(by, 0.0) + fmax(bz, 0.0) * fmax(bz, 0.0);
-        if (lb > tk.worst() * (1.0 + 1e-12)) continue;  // strictly farther: ties are still visited
-      }
-      const long long row = ((long long)z * g.ny + y) * g.nx;
-      const bool full = (r == 1) || dy == -r || dy == r || dz == -r || dz == r;
-      if (full) {
-        scan_range_k(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, tk);
-      } else {
-        if (x0 >= 0) scan_range_k(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, tk);
-        if (x1 < g.nx) scan_range_k(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, tk);
-      }
-    }
-    double guard = kInf;
-    if (x0 > 0) guard = fmin(guard, qx - (g.ox + x0 * g.h));
-    if (x1 < g.nx - 1) guard = fmin(guard, (g.ox + (x1 + 1) * g.h) - qx);
-    if (y0 > 0) guard = fmin(guard, qy - (g.oy + y0 * g.h));
-    if (y1 < g.ny - 1) guard = fmin(guard, (g.oy + (y1 + 1) * g.h) - qy);
-    if (z0 > 0) guard = fmin(guard, qz - (g.oz + z0 * g.h));
-    if (z1 < g.nz - 1) guard = fmin(guard, (g.oz + (z1 + 1) * g.h) - qz);
-    if (guard >= kInf) return;
-    guard -= 1e-9 * g.h;
-    if (tk.full() && guard > 0.0 && tk.worst() <= guard * guard) return;
-  }
-}
-
-__device__ __forceinline__ void knn_pca_body(const GridView& g, const double* __restrict__ fix_xyz,
-                                             const double* __restrict__ q_xyz, long long K, int k,
-                                             int sign_mode, float4* __restrict__ q_nrm,
-                                             long long* __restrict__ knn_idx,
-                                             double* __restrict__ knn_d2, const long long i) {
-  if (i >= K) return;
-  const double qx = q_xyz[3 * i + 0], qy = q_xyz[3 * i + 1], qz = q_xyz[3 * i + 2];
-  TopK tk;
-  tk.n = 0;
-  tk.k = k;
-  grid_knn(g, qx, qy, qz, tk);
-
-  // np.cov(pts.T, bias=False): subtract the mean, X X^T / (k - 1)
-  double mx = 0, my = 0, mz = 0;
-  for (int j = 0; j < tk.n; ++j) {
-    const long long p = tk.idx[j];
-    mx += fix_xyz[3 * p + 0];
-    my += fix_xyz[3 * p + 1];
-    mz += fix_xyz[3 * p + 2];
-    if (knn_idx) {
-      knn_idx[i * k + j] = p;
-      if (knn_d2) knn_d2[i * k + j] = tk.d2[j];
-    }
-  }
-  const double inv = 1.0 / (double)tk.n;
-  mx *= inv;
-  my *= inv;
-  mz *= inv;
-  double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-  for (int j = 0; j < tk.n; ++j) {
-    const long long p = tk.idx[j];
-    const double dx = fix_xyz[3 * p + 0] - mx, dy = fix_xyz[3 * p + 1] - my,
-                 dz = fix_xyz[3 * p + 2] - mz;
-    c00 = fma(dx, dx, c00);
-    c01 = fma(dx, dy, c01);
-    c02 = fma(dx, dz, c02);
-    c11 = fma(dy, dy, c11);
-    c12 = fma(dy, dz, c12);
-    c22 = fma(dz, dz, c22);
-  }
-  const double f = 1.0 / (double)(tk.n - 1);  // np.cov multiplies by true_divide(1, fact)
-  c00 *= f;
-  c01 *= f;
-  c02 *= f;
-  c11 *= f;
-  c12 *= f;
-  c22 *= f;
-
-  double w[3], n[3];
-  eig3_smallest(c00, c01, c02, c11, c12, c22, sign_mode, w, n);
-  // w sorted descending: planarity = (w1 - w2) / w0 (pointcloud.py:198), float32 store
-  float4 o;
-  o.x = (float)n[0];
-  o.y = (float)n[1];
-  o.z = (float)n[2];
-  o.w = (float)((w[1] - w[2]) / w[0]);
-  q_nrm[i] = o;
-}
 
 // =============================================================================================
 // Cooperative k-NN for k <= 16 (the reference's default is 10): MG lanes share one query.
@@ -223,23 +74,23 @@ __device__ __forceinline__ void lane_insert(const Rec* __restrict__ recs, LaneLi
 template <int KC>
 __device__ __forceinline__ void scan_range_l(const Rec* __restrict__ recs, uint32_t s, uint32_t e, double qx,
                                              double qy, double qz, double bound, LaneList<KC>& L) {
+  auto visit = [&](const Rec& r, uint32_t pos) {
+    const double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 <= bound) lane_insert<KC>(recs, L, d2, pos);
+  };
   for (uint32_t i = s; i < e; i += 4) {
+    // four 32-byte records in flight; the clamped tail repeats the last record, which is skipped
     const uint32_t last = e - 1;
     const uint32_t i1 = min(i + 1, last), i2 = min(i + 2, last), i3 = min(i + 3, last);
     const Rec r0 = recs[i];
     const Rec r1 = recs[i1];
     const Rec r2 = recs[i2];
     const Rec r3 = recs[i3];
-    const Rec* rr[4] = {&r0, &r1, &r2, &r3};
-    const uint32_t ii[4] = {i, i1, i2, i3};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j == 0 || ii[j] != ii[j - 1]) {  // the clamped tail repeats the last record: skip repeats
-        const double dx = rr[j]->x - qx, dy = rr[j]->y - qy, dz = rr[j]->z - qz;
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        if (d2 <= bound) lane_insert<KC>(recs, L, d2, ii[j]);
-      }
-    }
+    visit(r0, i);
+    if (i1 != i) visit(r1, i1);
+    if (i2 != i1) visit(r2, i2);
+    if (i3 != i2) visit(r3, i3);
   }
 }
 
@@ -347,6 +198,113 @@ __device__ __forceinline__ void knn_coop_body(const GridView& g, const double* _
   union_kth<MG, KC>(g.recs, L, k, gmask, sub, knn_pos + qi * k);
 }
 
+// One thread per query, 16 < k <= 64 (the reference's webots test uses k = 40): a sorted list of
+// record POSITIONS in a dynamically indexed (local-memory) array, ties by original index through
+// the records as everywhere, written to knn_pos for k_pca_from_knn.
+struct TopKPos {
+  double d2[kMaxK];
+  uint32_t pos[kMaxK];
+  int n, k;
+  __device__ __forceinline__ bool full() const { return n == k; }
+  __device__ __forceinline__ double worst() const { return d2[n - 1]; }
+  __device__ __forceinline__ void consider(const Rec* __restrict__ recs, double d, uint32_t p, long long idx) {
+    if (n == k) {
+      if (!(d < d2[k - 1] || (d == d2[k - 1] && idx < recs[pos[k - 1]].idx))) return;
+    } else {
+      ++n;
+    }
+    int j = n - 1;
+    while (j > 0 && (d2[j - 1] > d || (d2[j - 1] == d && recs[pos[j - 1]].idx > idx))) {
+      d2[j] = d2[j - 1];
+      pos[j] = pos[j - 1];
+      --j;
+    }
+    d2[j] = d;
+    pos[j] = p;
+  }
+};
+
+__device__ __forceinline__ void scan_range_kp(const Rec* __restrict__ recs, uint32_t s, uint32_t e, double qx,
+                                              double qy, double qz, TopKPos& tk) {
+  for (uint32_t i = s; i < e; i += 4) {
+    const uint32_t last = e - 1;
+    const Rec r0 = recs[i];
+    const Rec r1 = recs[min(i + 1, last)];
+    const Rec r2 = recs[min(i + 2, last)];
+    const Rec r3 = recs[min(i + 3, last)];
+    const int n = (int)min(4u, e - i);
+    const Rec* rr[4] = {&r0, &r1, &r2, &r3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < n) {
+        const double dx = rr[j]->x - qx, dy = rr[j]->y - qy, dz = rr[j]->z - qz;
+        tk.consider(recs, dx * dx + dy * dy + dz * dz, i + j, rr[j]->idx);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void knn_single_body(const GridView& g, const double* __restrict__ q_xyz, long long K,
+                                                int k, uint32_t* __restrict__ knn_pos, const long long i) {
+  if (i >= K) return;
+  const double qx = q_xyz[3 * i + 0], qy = q_xyz[3 * i + 1], qz = q_xyz[3 * i + 2];
+  TopKPos tk;
+  tk.n = 0;
+  tk.k = k;
+  const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+  const uint32_t* __restrict__ cs = g.cell_start;
+  for (int r = 1;; ++r) {
+    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
+    const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
+    const int side = 2 * r + 1, items = side * side, centre = items / 2;
+    for (int t0 = 0; t0 < items; ++t0) {
+      const int t = (r == 1) ? ((t0 == 0) ? centre : ((t0 <= centre) ? t0 - 1 : t0)) : t0;
+      const int dz = t / side - r, dy = t % side - r;
+      const int y = cy + dy, z = cz + dz;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      if (tk.full()) {
+        const double by = (dy < 0) ? qy - (g.oy + (y + 1) * g.h) : ((dy > 0) ? (g.oy + y * g.h) - qy : 0.0);
+        const double bz = (dz < 0) ? qz - (g.oz + (z + 1) * g.h) : ((dz > 0) ? (g.oz + z * g.h) - qz : 0.0);
+        const double lb = fmax(by, 0.0) * fmax(by, 0.0) + fmax(bz, 0.0) * fmax(bz, 0.0);
+        if (lb > tk.worst() * (1.0 + 1e-12)) continue;
+      }
+      const long long row = ((long long)z * g.ny + y) * g.nx;
+      const bool full = (r == 1) || dy == -r || dy == r || dz == -r || dz == r;
+      if (full) {
+        scan_range_kp(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, tk);
+      } else {
+        if (x0 >= 0) scan_range_kp(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, tk);
+        if (x1 < g.nx) scan_range_kp(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, tk);
+      }
+    }
+    double guard = kInf;
+    if (x0 > 0) guard = fmin(guard, qx - (g.ox + x0 * g.h));
+    if (x1 < g.nx - 1) guard = fmin(guard, (g.ox + (x1 + 1) * g.h) - qx);
+    if (y0 > 0) guard = fmin(guard, qy - (g.oy + y0 * g.h));
+    if (y1 < g.ny - 1) guard = fmin(guard, (g.oy + (y1 + 1) * g.h) - qy);
+    if (z0 > 0) guard = fmin(guard, qz - (g.oz + z0 * g.h));
+    if (z1 < g.nz - 1) guard = fmin(guard, (g.oz + (z1 + 1) * g.h) - qz);
+    if (guard >= kInf) break;
+    guard -= 1e-9 * g.h;
+    if (tk.full() && guard > 0.0 && tk.worst() <= guard * guard) break;
+  }
+  for (int j = 0; j < k; ++j) knn_pos[i * k + j] = (j < tk.n) ? tk.pos[j] : 0xffffffffu;
+}
+
+__global__ void __launch_bounds__(128)
+    k_knn_single(GridView g, const double* __restrict__ q_xyz, long long K, int k, uint32_t* __restrict__ knn_pos) {
+  knn_single_body(g, q_xyz, K, k, knn_pos, blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128)
+    k_knn_single_batch(const PairDev* __restrict__ pairs, const double* __restrict__ q_xyz, int k, long long Kmax,
+                       uint32_t* __restrict__ knn_pos) {
+  const PairDev pd = pairs[blockIdx.y];
+  knn_single_body(pd.gfix, q_xyz + 3 * pd.q_off, pd.K, k, knn_pos + (size_t)blockIdx.y * Kmax * k,
+                  blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+
 template <int MG, int KC>
 __global__ void __launch_bounds__(128)
     k_knn_coop(GridView g, const double* __restrict__ q_xyz, long long K, int k, uint32_t* __restrict__ knn_pos) {
@@ -419,6 +377,89 @@ __global__ void __launch_bounds__(128)
                     blockIdx.x * (long long)blockDim.x + threadIdx.x);
 }
 
+// One thread per query with the list in REGISTERS (k <= KC <= 16): the insertion network of the
+// cooperative kernel, one list per query (a third of the insertions of four lane lists, no
+// merge rounds), no local-memory frame.  The machine is full at K >= ~16 000 queries anyway, so
+// the per-thread chain of loads is hidden by the other warps: this is the kernel for large K.
+template <int KC>
+__device__ __forceinline__ double list_kth(const LaneList<KC>& L, int k) {
+  double v = kInf;
+#pragma unroll
+  for (int j = 0; j < KC; ++j)
+    if (j == k - 1) v = L.d[j];
+  return v;
+}
+
+template <int KC>
+__device__ __forceinline__ void knn_reg_body(const GridView& g, const double* __restrict__ q_xyz, long long K,
+                                             int k, uint32_t* __restrict__ knn_pos, const long long i) {
+  if (i >= K) return;
+  const double qx = q_xyz[3 * i + 0], qy = q_xyz[3 * i + 1], qz = q_xyz[3 * i + 2];
+  const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+  const uint32_t* __restrict__ cs = g.cell_start;
+  LaneList<KC> L;
+#pragma unroll
+  for (int j = 0; j < KC; ++j) {
+    L.d[j] = kInf;
+    L.p[j] = 0xffffffffu;
+  }
+  for (int r = 1;; ++r) {
+    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r, z0 = cz - r, z1 = cz + r;
+    const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
+    const int side = 2 * r + 1, items = side * side, centre = items / 2;
+    for (int t0 = 0; t0 < items; ++t0) {
+      // the centre row first in ring 1: the list fills with near points, later rows are pruned
+      const int t = (r == 1) ? ((t0 == 0) ? centre : ((t0 <= centre) ? t0 - 1 : t0)) : t0;
+      const int dz = t / side - r, dy = t % side - r;
+      const int y = cy + dy, z = cz + dz;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      const double lim = list_kth<KC>(L, k) * (1.0 + 1e-12);  // k-th best so far (inf until k are known)
+      const double by = (dy < 0) ? qy - (g.oy + (y + 1) * g.h) : ((dy > 0) ? (g.oy + y * g.h) - qy : 0.0);
+      const double bz = (dz < 0) ? qz - (g.oz + (z + 1) * g.h) : ((dz > 0) ? (g.oz + z * g.h) - qz : 0.0);
+      const double lb = fmax(by, 0.0) * fmax(by, 0.0) + fmax(bz, 0.0) * fmax(bz, 0.0);
+      if (lb > lim) continue;  // strictly farther: ties are still visited
+      const long long row = ((long long)z * g.ny + y) * g.nx;
+      const bool full = (r == 1) || dy == -r || dy == r || dz == -r || dz == r;
+      if (full) {
+        scan_range_l<KC>(g.recs, cs[row + xa], cs[row + xb + 1], qx, qy, qz, lim, L);
+      } else {
+        if (x0 >= 0) scan_range_l<KC>(g.recs, cs[row + x0], cs[row + x0 + 1], qx, qy, qz, lim, L);
+        if (x1 < g.nx) scan_range_l<KC>(g.recs, cs[row + x1], cs[row + x1 + 1], qx, qy, qz, lim, L);
+      }
+    }
+    double guard = kInf;
+    if (x0 > 0) guard = fmin(guard, qx - (g.ox + x0 * g.h));
+    if (x1 < g.nx - 1) guard = fmin(guard, (g.ox + (x1 + 1) * g.h) - qx);
+    if (y0 > 0) guard = fmin(guard, qy - (g.oy + y0 * g.h));
+    if (y1 < g.ny - 1) guard = fmin(guard, (g.oy + (y1 + 1) * g.h) - qy);
+    if (z0 > 0) guard = fmin(guard, qz - (g.oz + z0 * g.h));
+    if (z1 < g.nz - 1) guard = fmin(guard, (g.oz + (z1 + 1) * g.h) - qz);
+    if (guard >= kInf) break;
+    guard -= 1e-9 * g.h;
+    const double kth = list_kth<KC>(L, k);
+    if (kth < kInf && guard > 0.0 && kth <= guard * guard) break;
+  }
+#pragma unroll
+  for (int j = 0; j < KC; ++j)
+    if (j < k) knn_pos[i * k + j] = L.p[j];
+}
+
+template <int KC>
+__global__ void __launch_bounds__(128)
+    k_knn_reg(GridView g, const double* __restrict__ q_xyz, long long K, int k, uint32_t* __restrict__ knn_pos) {
+  knn_reg_body<KC>(g, q_xyz, K, k, knn_pos, blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+template <int KC>
+__global__ void __launch_bounds__(128)
+    k_knn_reg_batch(const PairDev* __restrict__ pairs, const double* __restrict__ q_xyz, int k, long long Kmax,
+                    uint32_t* __restrict__ knn_pos) {
+  const PairDev pd = pairs[blockIdx.y];
+  knn_reg_body<KC>(pd.gfix, q_xyz + 3 * pd.q_off, pd.K, k, knn_pos + (size_t)blockIdx.y * Kmax * k,
+                   blockIdx.x * (long long)blockDim.x + threadIdx.x);
+}
+
 // batched forms: blockIdx.y = pair
 template <int MG, int KC>
 __global__ void __launch_bounds__(128)
@@ -434,23 +475,6 @@ __global__ void __launch_bounds__(128)
   const PairDev pd = pairs[blockIdx.y];
   pca_from_knn_body(pd.gfix, q_xyz + 3 * pd.q_off, pd.K, k, sign_mode, knn_pos + (size_t)blockIdx.y * Kmax * k,
                     q_nrm + pd.q_off, nullptr, nullptr, blockIdx.x * (long long)blockDim.x + threadIdx.x);
-}
-
-__global__ void __launch_bounds__(128)
-    k_knn_pca(GridView g, const double* __restrict__ fix_xyz, const double* __restrict__ q_xyz,
-              long long K, int k, int sign_mode, float4* __restrict__ q_nrm,
-              long long* __restrict__ knn_idx, double* __restrict__ knn_d2) {
-  knn_pca_body(g, fix_xyz, q_xyz, K, k, sign_mode, q_nrm, knn_idx, knn_d2,
-               blockIdx.x * (long long)blockDim.x + threadIdx.x);
-}
-
-// batched: blockIdx.y = pair; neighbour indices are local to the pair's fixed cloud
-__global__ void __launch_bounds__(128)
-    k_knn_pca_batch(const PairDev* __restrict__ pairs, const double* __restrict__ fix_xyz,
-                    const double* __restrict__ q_xyz, int k, int sign_mode, float4* __restrict__ q_nrm) {
-  const PairDev pd = pairs[blockIdx.y];
-  knn_pca_body(pd.gfix, fix_xyz + 3 * pd.fix_off, q_xyz + 3 * pd.q_off, pd.K, k, sign_mode,
-               q_nrm + pd.q_off, nullptr, nullptr, blockIdx.x * (long long)blockDim.x + threadIdx.x);
 }
 
 }  // namespace
@@ -471,12 +495,15 @@ void estimate_normals_launch(Ctx& c, int k) {
     kd2 = c.knn_d2.p;
   }
   c.knn_k = c.keep_knn ? k : 0;
-  if (k <= 16 && c.knn_coop) {
-    c.knn_pos.reserve((size_t)c.K * k);
-    // lanes per query: 8 while there are few queries (latency-bound), 4 once they fill the machine
+  // Both k-NN kernels hand record positions to k_pca_from_knn.  knn_coop: 1 = cooperative lanes
+  // (k <= 16), 0 = one thread per query, -1 (default) = cooperative while the search is
+  // latency-bound (few queries), one thread per query once the queries fill the machine.
+  const bool coop = (k <= 16) && (c.knn_coop == 1 || (c.knn_coop < 0 && c.K <= 16384));
+  c.knn_pos.reserve((size_t)c.K * k);
+  const GridView g = c.gfix.view();
+  if (coop) {
     const int mg = (c.K <= 32768) ? 8 : 4;
     const unsigned blocks = (unsigned)((c.K * mg + 127) / 128);
-    const GridView g = c.gfix.view();
     if (mg == 8) {
       if (k <= 12) k_knn_coop<8, 12><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
       else k_knn_coop<8, 16><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
@@ -484,43 +511,43 @@ void estimate_normals_launch(Ctx& c, int k) {
       if (k <= 12) k_knn_coop<4, 12><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
       else k_knn_coop<4, 16><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
     }
-    k_pca_from_knn<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.sign_mode,
-                                                                        c.knn_pos.p, c.q_nrm.p, kidx, kd2);
-    SICP_CUDA(cudaGetLastError());
-    c.tm.kernel_launches += 2;
-    return;
+  } else if (k <= 12) {
+    k_knn_reg<12><<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
+  } else if (k <= 16) {
+    k_knn_reg<16><<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
+  } else {
+    k_knn_single<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
   }
-  k_knn_pca<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(
-      c.gfix.view(), c.fix_xyz.p, c.q_xyz.p, c.K, k, c.sign_mode, c.q_nrm.p, kidx, kd2);
+  k_pca_from_knn<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.sign_mode,
+                                                                      c.knn_pos.p, c.q_nrm.p, kidx, kd2);
   SICP_CUDA(cudaGetLastError());
-  c.tm.kernel_launches += 1;
+  c.tm.kernel_launches += 2;
 }
 
 void batch_normals_launch(Ctx& c, Batch& b, int k) {
   SICP_REQUIRE(k >= 2 && k <= kMaxK, SICP_ERR_BAD_ARG,
                "neighbors must be between 2 and 64 (got " + std::to_string(k) + ")");
-  if (k <= 16 && c.knn_coop) {
-    b.knn_pos.reserve((size_t)b.n_pairs * b.Kmax * k);
-    const long long total = b.Kmax * b.n_pairs;
-    const int mg = (total <= 32768) ? 8 : 4;
-    const dim3 grid((unsigned)((b.Kmax * mg + 127) / 128), b.n_pairs);
-    if (mg == 8) {
-      if (k <= 12) k_knn_coop_batch<8, 12><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
-      else k_knn_coop_batch<8, 16><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
-    } else {
-      if (k <= 12) k_knn_coop_batch<4, 12><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
-      else k_knn_coop_batch<4, 16><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
-    }
-    k_pca_from_knn_batch<<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
-        b.pairs.p, b.q_xyz.p, k, b.Kmax, c.sign_mode, b.knn_pos.p, b.q_nrm.p);
-    SICP_CUDA(cudaGetLastError());
-    c.tm.kernel_launches += 2;
-    return;
+  const long long total = b.Kmax * b.n_pairs;
+  const bool coop = (k <= 16) && (c.knn_coop == 1 || (c.knn_coop < 0 && total <= 16384));
+  b.knn_pos.reserve((size_t)b.n_pairs * b.Kmax * k);
+  if (coop) {
+    const dim3 grid((unsigned)((b.Kmax * 8 + 127) / 128), b.n_pairs);
+    if (k <= 12) k_knn_coop_batch<8, 12><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
+    else k_knn_coop_batch<8, 16><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
+  } else if (k <= 12) {
+    k_knn_reg_batch<12><<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
+        b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
+  } else if (k <= 16) {
+    k_knn_reg_batch<16><<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
+        b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
+  } else {
+    k_knn_single_batch<<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
+        b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
   }
-  k_knn_pca_batch<<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
-      b.pairs.p, b.fix_xyz.p, b.q_xyz.p, k, c.sign_mode, b.q_nrm.p);
+  k_pca_from_knn_batch<<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
+      b.pairs.p, b.q_xyz.p, k, b.Kmax, c.sign_mode, b.knn_pos.p, b.q_nrm.p);
   SICP_CUDA(cudaGetLastError());
-  c.tm.kernel_launches += 1;
+  c.tm.kernel_launches += 2;
 }
 
 }  // namespace sicp

@@ -739,12 +739,17 @@ def test_barrier_free_kernel_equals_cooperative_kernel(gpu, name, kw):
     print(f"{name} {kw}: fused iterations {ta['fused_iterations']} of {a.iterations}, re-run {ta['rerun_iterations']}, "
           f"|dH| = {np.linalg.norm(a.H - b.H):.2e}")
     assert tb["fused_iterations"] == 0
-    assert ta["fused_iterations"] + ta["rerun_iterations"] == a.iterations - 1
-    assert ta["fused_iterations"] >= (a.iterations - 1) // 2
+    if kw.get("correspondences", 1000) <= 4096:
+        # one block owns the problem: every iteration (the first included) runs in k_rs_fused
+        assert ta["fused_iterations"] == a.iterations and ta["rerun_iterations"] == 0
+    else:
+        assert ta["fused_iterations"] + ta["rerun_iterations"] == a.iterations - 1
+        assert ta["fused_iterations"] >= (a.iterations - 1) // 2
     assert a.iterations == b.iterations and a.converged == b.converged
     assert [r["n_kept"] for r in a.records] == [r["n_kept"] for r in b.records]
     for ra, rb in zip(a.records, b.records):
-        assert ra["median"] == rb["median"] and ra["mad"] == rb["mad"]  # exact order statistics
+        # exact order statistics of distances that differ by the rounding of the two summation orders
+        np.testing.assert_allclose([ra["median"], ra["mad"]], [rb["median"], rb["mad"]], rtol=1e-9, atol=1e-15)
         np.testing.assert_allclose(ra["std_res"], rb["std_res"], rtol=1e-7)
         np.testing.assert_allclose(ra["mean_res"], rb["mean_res"], rtol=1e-5, atol=1e-12)
     np.testing.assert_allclose(a.H, b.H, rtol=0, atol=1e-11)

@@ -97,7 +97,26 @@ def small(name, kw):
                   f"({r.loop_ms/r.iterations*1e3:.1f} us/it), fused {tm['fused_iterations']} re-run {tm['rerun_iterations']}")
 
 
+def normals_probe():
+    from conftest import load_pair
+
+    for name, n, K in (("C3", 1_000_000, 100_000), ("dragon", 0, 1000)):
+        if name == "C3":
+            X_fix, X_mov, _ = make_pair(n, 0)
+        else:
+            X_fix, X_mov = load_pair(name)
+        with _capi.Engine() as e:
+            e.set_clouds(X_fix, X_mov)
+            e.set_selected(sb.pointcloud.subsample_indices(X_fix.shape[0], K).astype(np.int64))
+            for mode in (1, 0, -1):
+                e.set_option("knn_coop", mode)
+                e.estimate_normals(10, download=False)
+                e.estimate_normals(10, download=False)
+                print(f"normals {name} K={K} knn_coop={mode}: {e.timings()['normals_ms'] * 1e3:.1f} us")
+
+
 if __name__ == "__main__":
+    normals_probe()
     c3()
     small("dragon", {})
     small("bunny", {"max_overlap_distance": 1.0})
