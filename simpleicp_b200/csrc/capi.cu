@@ -303,7 +303,7 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
   } else if (k == "keep_knn") {
     c.keep_knn = (value != 0) ? 1 : 0;
   } else if (k == "knn_coop") {
-    c.knn_coop = (value < 0) ? -1 : ((value != 0) ? 1 : 0);
+    c.knn_coop = (value < 0) ? -1 : ((value >= 2) ? 2 : ((value != 0) ? 1 : 0));
   } else if (k == "sphere_scan") {
     c.sphere_scan = (value != 0) ? 1 : 0;
   } else if (k == "warm_start") {

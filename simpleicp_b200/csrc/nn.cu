@@ -253,7 +253,7 @@ __device__ __forceinline__ void match_coop_body(
     const int za = cell_coord(qz - R, g.oz, g.inv_h, g.nz), zb = cell_coord(qz + R, g.oz, g.inv_h, g.nz);
     const int nyb = yb - ya + 1;
     const long long rows = (long long)nyb * (zb - za + 1);
-    if (rows > 8 * MG) return false;
+    if (rows > 64 * MG) return false;  // ~15 instructions per pruned row: cheaper than the next rings up to here
     for (int t = sub; t < (int)rows; t += MG) {
       const int zz = za + t / nyb, yy = ya + t % nyb;
       const double ylo = g.oy + yy * g.h, zlo = g.oz + zz * g.h;
@@ -406,6 +406,39 @@ __device__ __forceinline__ void match_coop_body(
     if (cap2 >= 0.0 && (best < cap2 || (guard > 0.0 && guard * guard >= cap2))) {
       resolved = true;  // overlap filter: the side of the bound is decided (see grid_nn)
       break;
+    }
+    // Nothing within the 27 cells (first iteration of a registration: the clouds are still apart
+    // by several cells, typically along the surface normal).  A cube grown ring by ring meets a
+    // sheet-like surface with a whole FACE at once — hundreds of candidates at ring r, thousands
+    // of cell-table reads before it.  Probe outwards along the three axes instead (six cells per
+    // step): a surface at distance D crosses one of the axes within sqrt(3) D, the first point
+    // found bounds the search, and the sphere scan below finishes it.
+    if (use_sphere && r == 1 && best == kInf) {
+      for (int s2 = 2; s2 <= 96; ++s2) {
+        bool any_inside = false;
+        for (int t = sub; t < 6; t += MG) {
+          const int axis = t >> 1, off = (t & 1) ? s2 : -s2;
+          const int x = cx + (axis == 0 ? off : 0), y = cy + (axis == 1 ? off : 0), z = cz + (axis == 2 ? off : 0);
+          if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+          any_inside = true;
+          const long long cell = ((long long)z * g.ny + y) * g.nx + x;
+          scan_range(g.recs, cs[cell], cs[cell + 1], qx, qy, qz, best, bidx, bpos);
+        }
+        unsigned int inside = any_inside ? 1u : 0u;
+#pragma unroll
+        for (int o = MG / 2; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(gmask, best, o, MG);
+          const long long oi = __shfl_xor_sync(gmask, bidx, o, MG);
+          const uint32_t op = __shfl_xor_sync(gmask, bpos, o, MG);
+          inside |= __shfl_xor_sync(gmask, inside, o, MG);
+          if (od < best || (od == best && oi >= 0 && (bidx < 0 || oi < bidx))) {
+            best = od;
+            bidx = oi;
+            bpos = op;
+          }
+        }
+        if (best < kInf || !inside) break;
+      }
     }
     // a point is known now: finish inside its sphere instead of growing the cube ring by ring
     // (best is uniform across the group after the reduction, so the whole group takes one branch)

@@ -495,10 +495,15 @@ void estimate_normals_launch(Ctx& c, int k) {
     kd2 = c.knn_d2.p;
   }
   c.knn_k = c.keep_knn ? k : 0;
-  // Both k-NN kernels hand record positions to k_pca_from_knn.  knn_coop: 1 = cooperative lanes
-  // (k <= 16), 0 = one thread per query, -1 (default) = cooperative while the search is
-  // latency-bound (few queries), one thread per query once the queries fill the machine.
+  // All k-NN kernels hand record positions to k_pca_from_knn.  knn_coop: 1 = cooperative lanes
+  // (k <= 16), 0 = one thread per query with the list in local memory, 2 = one thread per query
+  // with the list in registers (k <= 16), -1 (default) = cooperative while the search is
+  // latency-bound (few queries: 80 us vs 200 us at K = 1000), one thread per query with the
+  // local-memory list once the queries fill the machine (K = 100 000, k = 10: 310 us; register
+  // list 425 us, cooperative 506 us — the fixed-length insertion network costs more than the
+  // early-exit loop saves in memory traffic; profiles/README.md).
   const bool coop = (k <= 16) && (c.knn_coop == 1 || (c.knn_coop < 0 && c.K <= 16384));
+  const bool reg = (k <= 16) && c.knn_coop == 2;
   c.knn_pos.reserve((size_t)c.K * k);
   const GridView g = c.gfix.view();
   if (coop) {
@@ -511,9 +516,9 @@ void estimate_normals_launch(Ctx& c, int k) {
       if (k <= 12) k_knn_coop<4, 12><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
       else k_knn_coop<4, 16><<<blocks, 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
     }
-  } else if (k <= 12) {
+  } else if (reg && k <= 12) {
     k_knn_reg<12><<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
-  } else if (k <= 16) {
+  } else if (reg) {
     k_knn_reg<16><<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
   } else {
     k_knn_single<<<(unsigned)((c.K + 127) / 128), 128, 0, c.stream>>>(g, c.q_xyz.p, c.K, k, c.knn_pos.p);
@@ -529,15 +534,16 @@ void batch_normals_launch(Ctx& c, Batch& b, int k) {
                "neighbors must be between 2 and 64 (got " + std::to_string(k) + ")");
   const long long total = b.Kmax * b.n_pairs;
   const bool coop = (k <= 16) && (c.knn_coop == 1 || (c.knn_coop < 0 && total <= 16384));
+  const bool reg = (k <= 16) && c.knn_coop == 2;
   b.knn_pos.reserve((size_t)b.n_pairs * b.Kmax * k);
   if (coop) {
     const dim3 grid((unsigned)((b.Kmax * 8 + 127) / 128), b.n_pairs);
     if (k <= 12) k_knn_coop_batch<8, 12><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
     else k_knn_coop_batch<8, 16><<<grid, 128, 0, c.stream>>>(b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
-  } else if (k <= 12) {
+  } else if (reg && k <= 12) {
     k_knn_reg_batch<12><<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
         b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
-  } else if (k <= 16) {
+  } else if (reg) {
     k_knn_reg_batch<16><<<dim3((unsigned)((b.Kmax + 127) / 128), b.n_pairs), 128, 0, c.stream>>>(
         b.pairs.p, b.q_xyz.p, k, b.Kmax, b.knn_pos.p);
   } else {

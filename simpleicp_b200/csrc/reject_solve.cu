@@ -61,6 +61,7 @@ struct Shared {
   double M[13][13];
   double J[13][6];
   double th[13];
+  double th_in[13];  // theta of the transform the distances were evaluated at (re-centred model)
   double B[13][7];
   double A[36];
   double g[6];
@@ -391,8 +392,23 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
   n1_out = n1;
 }
 
+// theta of an affine map p -> A p + b in the centred frame: [rows of A with b'_a after each, 1],
+// b' = A c_m + b - c_f.  Lanes 0..12 return their entry.
+__device__ __forceinline__ double theta_entry(const Rigid& T, const double* cm, const double* cf, int e) {
+  if (e >= 12) return 1.0;
+  const int r = e >> 2, c = e & 3;
+  if (c < 3) return T.r[r * 3 + c];
+  return T.r[r * 3 + 0] * cm[0] + T.r[r * 3 + 1] * cm[1] + T.r[r * 3 + 2] * cm[2] + T.t[r] - cf[r];
+}
+
 // --- Levenberg-Marquardt on the 13 x 13 moment matrix (warp 0 of block 0) -------------------
-// theta(x) = [R(alpha) row-wise with t'_a after each row, 1], t' = R c_m + t - c_f.
+// Re-centred linear model.  With T_in the transform the match evaluated the distances d_i at,
+//   r_i(T) = n_i . (T p_i - q_i) = d_i + n_i . ((A - A_in) u_i + (b' - b'_in)),   u_i = p_i - c_m,
+// i.e. r_i = phi_i . theta with phi_i = [n_i (x) (u_i, 1), d_i] and
+//   theta(x) = [R(alpha) row-wise with t'_a after each row, 1] - [theta(T_in), 0],  t' = R c_m + t - c_f.
+// M = sum phi phi^T.  Near the solution theta is (tiny, ..., tiny, 1): sum r^2 = theta^T M theta is
+// dominated by sum d^2 and carries no cancellation (the un-centred form phi = [.., -n.q'] loses
+// (|q'| / |r|)^2 ~ 1e9 on millimetre residuals over metre-sized clouds).
 // Everything here is a serial dependency chain executed by ONE warp while the rest of the grid
 // waits at a barrier, so the code is organised to keep that chain short: the three sincos run on
 // three lanes, the matrix products are spread over the lanes, and the 6 x 6 factorisation is a
@@ -425,13 +441,14 @@ __device__ __noinline__ void lm_eval(Shared& s, const double* x, const double* c
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        s.th[a * 4 + b] = R[a * 3 + b];
+        s.th[a * 4 + b] = R[a * 3 + b] - s.th_in[a * 4 + b];
 #pragma unroll
         for (int k = 0; k < 3; ++k) s.J[a * 4 + b][k] = D[k][a * 3 + b];
 #pragma unroll
         for (int k = 3; k < 6; ++k) s.J[a * 4 + b][k] = 0.0;
       }
-      s.th[a * 4 + 3] = R[a * 3 + 0] * cm[0] + R[a * 3 + 1] * cm[1] + R[a * 3 + 2] * cm[2] + x[3 + a] - cf[a];
+      s.th[a * 4 + 3] = (R[a * 3 + 0] * cm[0] + R[a * 3 + 1] * cm[1] + R[a * 3 + 2] * cm[2] + x[3 + a] - cf[a]) -
+                        s.th_in[a * 4 + 3];
 #pragma unroll
       for (int k = 0; k < 3; ++k)
         s.J[a * 4 + 3][k] = D[k][a * 3 + 0] * cm[0] + D[k][a * 3 + 1] * cm[1] + D[k][a * 3 + 2] * cm[2];
@@ -690,7 +707,9 @@ __device__ void lin_solve(Shared& s, const Rigid& Tc, const double* cf, int lane
   }
   if (lane < 13) {
     const int a = lane / 4, b = lane % 4;
-    s.th[lane] = (lane == 12) ? 1.0 : ((b < 3) ? Tc.r[a * 3 + b] : 0.0);
+    (void)a;
+    (void)b;
+    s.th[lane] = (lane == 12) ? 1.0 : 0.0;  // re-centred model: theta(x) - theta(T_c) = J x
   }
   __syncwarp();
   moment_products(s, lane);
@@ -986,9 +1005,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     auto accumulate = [&](const float4 nr, const double d, const double p0, const double p1,
                           const double p2, const double f0, const double f1, const double f2) {
       const double u0 = p0 - cm[0], u1 = p1 - cm[1], u2 = p2 - cm[2];
-      const double q0 = f0 - cf[0], q1 = f1 - cf[1], q2 = f2 - cf[2];
+      (void)f0;
+      (void)f1;
+      (void)f2;
       const double n0 = (double)nr.x, n1d = (double)nr.y, n2 = (double)nr.z;
-      const double sc = -(n0 * q0 + n1d * q1 + n2 * q2);
+      const double sc = d;  // re-centred model: the scalar entry of phi is the distance itself
       double na, nb, nv;
       if (role == 0) {
         na = n0 * n0; nb = n0 * n1d; nv = n0;
@@ -1109,6 +1130,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       }
       s.M[r][c] = v;
     }
+    if (tid < 13) s.th_in[tid] = (tid == 12) ? 0.0 : theta_entry(Tin, cm, cf, tid);
     __syncthreads();
     RS_STAMP(18);
     if (warp == 0) {
@@ -1523,15 +1545,6 @@ __device__ bool fused_select(SharedF& sf, const RSArgs& a, RSWork wk, const DevS
   return true;
 }
 
-// theta of an affine map p -> A p + b in the centred frame: [rows of A with b'_a after each, 1],
-// b' = A c_m + b - c_f.  Lanes 0..12 return their entry.
-__device__ __forceinline__ double theta_entry(const Rigid& T, const double* cm, const double* cf, int e) {
-  if (e >= 12) return 1.0;
-  const int r = e >> 2, c = e & 3;
-  if (c < 3) return T.r[r * 3 + c];
-  return T.r[r * 3 + 0] * cm[0] + T.r[r * 3 + 1] * cm[1] + T.r[r * 3 + 2] * cm[2] + T.t[r] - cf[r];
-}
-
 __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int bid, SharedF& sf) {
   Shared& s = sf.s;
   DevState* st = a.state;
@@ -1577,13 +1590,14 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
     const float4* __restrict__ qn = a.q_nrm;
     const double* __restrict__ dd = a.dist;
     const double* __restrict__ mv = a.m_xyz;
-    const double* __restrict__ qx = a.q_xyz;
     auto accumulate = [&](const float4 nr, const double d, const double p0, const double p1,
                           const double p2, const double f0, const double f1, const double f2) {
       const double u0 = p0 - cm[0], u1 = p1 - cm[1], u2 = p2 - cm[2];
-      const double q0 = f0 - cf[0], q1 = f1 - cf[1], q2 = f2 - cf[2];
+      (void)f0;
+      (void)f1;
+      (void)f2;
       const double n0 = (double)nr.x, n1d = (double)nr.y, n2 = (double)nr.z;
-      const double sc = -(n0 * q0 + n1d * q1 + n2 * q2);
+      const double sc = d;  // re-centred model: the scalar entry of phi is the distance itself
       double na, nb, nv;
       if (role == 0) {
         na = n0 * n0; nb = n0 * n1d; nv = n0;
@@ -1627,12 +1641,10 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
       const double dA = dd[i], dB = dd[jb];
       const double pA0 = mv[3 * i + 0], pA1 = mv[3 * i + 1], pA2 = mv[3 * i + 2];
       const double pB0 = mv[3 * jb + 0], pB1 = mv[3 * jb + 1], pB2 = mv[3 * jb + 2];
-      const double fA0 = qx[3 * i + 0], fA1 = qx[3 * i + 1], fA2 = qx[3 * i + 2];
-      const double fB0 = qx[3 * jb + 0], fB1 = qx[3 * jb + 1], fB2 = qx[3 * jb + 2];
       const bool kA = ((double)nrA.w >= a.min_planarity) && (fabs(dA - median) <= lim);
       const bool kB = hb && ((double)nrB.w >= a.min_planarity) && (fabs(dB - median) <= lim);
-      if (kA) accumulate(nrA, dA, pA0, pA1, pA2, fA0, fA1, fA2);
-      if (kB) accumulate(nrB, dB, pB0, pB1, pB2, fB0, fB1, fB2);
+      if (kA) accumulate(nrA, dA, pA0, pA1, pA2, 0.0, 0.0, 0.0);
+      if (kB) accumulate(nrB, dB, pB0, pB1, pB2, 0.0, 0.0, 0.0);
       if (role == 0) {
         a.keep[i] = kA ? 1 : 0;
         if (hb) a.keep[ib] = kB ? 1 : 0;
@@ -1738,6 +1750,8 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
   __syncthreads();
   if (tid == 0) wk.phase_t[18] = global_timer_ns();
   if (warp != 0) return;
+  if (lane < 13) s.th_in[lane] = (lane == 12) ? 0.0 : theta_entry(Tin, cm, cf, lane);
+  __syncwarp();
 
   const long long n_kept = (long long)(sf.totf[0 * RSF_NACC + 25] + 0.5);
   const double sum_d = sf.totf[1 * RSF_NACC + 24], sum_d2 = sf.totf[1 * RSF_NACC + 25];
@@ -1802,7 +1816,7 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
     T_res = T_new;
   }
   // residual statistics at the solution from the moments: r_i = phi_i . theta
-  const double th = theta_entry(T_res, cm, cf, min(lane, 12));
+  const double th = theta_entry(T_res, cm, cf, min(lane, 12)) - s.th_in[min(lane, 12)];
   double rowdot = 0.0, s1 = 0.0;
   if (lane < 13) {
 #pragma unroll

@@ -108,7 +108,7 @@ def normals_probe():
         with _capi.Engine() as e:
             e.set_clouds(X_fix, X_mov)
             e.set_selected(sb.pointcloud.subsample_indices(X_fix.shape[0], K).astype(np.int64))
-            for mode in (1, 0, -1):
+            for mode in (1, 0, 2, -1):
                 e.set_option("knn_coop", mode)
                 e.estimate_normals(10, download=False)
                 e.estimate_normals(10, download=False)
