@@ -74,8 +74,8 @@ __device__ __forceinline__ void lane_insert(const Rec* __restrict__ recs, LaneLi
 template <int KC>
 __device__ __forceinline__ void scan_range_l(const Rec* __restrict__ recs, uint32_t s, uint32_t e, double qx,
                                              double qy, double qz, double bound, LaneList<KC>& L) {
-  auto visit = [&](const Rec& r, uint32_t pos) {
-    const double dx = r.x - qx, dy = r.y - qy, dz = r.z - qz;
+  auto visit = [&](const double rx, const double ry, const double rz, uint32_t pos) {
+    const double dx = rx - qx, dy = ry - qy, dz = rz - qz;
     const double d2 = dx * dx + dy * dy + dz * dz;
     if (d2 <= bound) lane_insert<KC>(recs, L, d2, pos);
   };
@@ -87,10 +87,10 @@ __device__ __forceinline__ void scan_range_l(const Rec* __restrict__ recs, uint3
     const Rec r1 = recs[i1];
     const Rec r2 = recs[i2];
     const Rec r3 = recs[i3];
-    visit(r0, i);
-    if (i1 != i) visit(r1, i1);
-    if (i2 != i1) visit(r2, i2);
-    if (i3 != i2) visit(r3, i3);
+    visit(r0.x, r0.y, r0.z, i);
+    if (i1 != i) visit(r1.x, r1.y, r1.z, i1);
+    if (i2 != i1) visit(r2.x, r2.y, r2.z, i2);
+    if (i3 != i2) visit(r3.x, r3.y, r3.z, i3);
   }
 }
 

@@ -1295,6 +1295,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
     if (lane == 0) {
       rec->mean_res = mean;
       rec->std_res = sd;
+      // Predictor of the NEXT iteration's order statistics: the residuals at the new transform, not
+      // the distances this iteration started from — the first solves of a registration shrink the
+      // distribution several-fold, and the next match finds (mostly) these very correspondences.
+      // median ~ mean, MAD ~ 0.8 std of the kept residuals (truncated at 3 MAD ~ 2 sigma).
+      if (sd > 0.0 && isfinite(sd) && isfinite(mean)) {
+        st->pred_med = mean;
+        st->pred_mad = 0.8 * sd;
+        st->pred_valid = 1;
+      }
       st->T = st->T_new;
       st->Tinv = rigid_inverse(st->T_new);
       if (!a.variant) st->H_rep = st->T_new;
@@ -1871,6 +1880,12 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
     st->Tinv = rigid_inverse(T_new);
     rec->mean_res = mean;
     rec->std_res = sd;
+    // predictor of the next iteration from the residuals at the new transform (see k_reject_solve)
+    if (sd > 0.0 && isfinite(sd) && isfinite(mean)) {
+      st->pred_med = mean;
+      st->pred_mad = 0.8 * sd;
+      st->pred_valid = 1;
+    }
     st->prev_mean = mean;
     st->prev_std = sd;
     st->iterations_done = a.it + 1;

@@ -1,6 +1,6 @@
 """Turn the ncu outputs in gpurun_out/ into the tracked summaries under profiles/.
 
-    python tools/summarize_profiles.py <launch_list.csv> <full_capture.ncu-rep> <tag>
+    python tools/summarize_profiles.py <launch_list.csv> <full_capture.ncu-rep>[,<more.ncu-rep>...] <tag>
 
 Writes profiles/<tag>_launches.md (per-kernel totals and shares of the step), profiles/<tag>_kernels.md
 (key metrics of every captured launch) and profiles/ncu_traffic.json (DRAM bytes per launch of
@@ -28,12 +28,12 @@ agg = collections.OrderedDict()
 for n, us in seq:
     a = agg.setdefault(n, [0, 0.0, 1e30, 0.0]); a[0] += 1; a[1] += us; a[2] = min(a[2], us); a[3] = max(a[3], us)
 # steady-state step = last (match, [bf, bf_finalize], reject_solve) groups
-steady = [(n, us) for n, us in seq if n.startswith(("k_match_grid", "k_reject_solve", "k_bf_"))]
+steady = [(n, us) for n, us in seq if n.startswith(("k_match_grid", "k_reject_solve", "k_rs_fused", "k_bf_"))]
 tail = steady[-40:]
 step_us = collections.defaultdict(float); step_n = collections.Counter()
 for n, us in tail:
     step_us[n] += us; step_n[n] += 1
-n_steps = max(step_n.get("k_reject_solve<1>", 0) or max(step_n.values()), 1)
+n_steps = max(step_n.get("k_rs_fused", 0) or step_n.get("k_reject_solve<1>", 0) or max(step_n.values()), 1)
 tot = sum(step_us.values())
 out = [f"# {tag}: ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold caches, serialised)\n",
        "Command: `python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1` under ncu; absolute times are",
@@ -46,17 +46,15 @@ for n, t in sorted(step_us.items(), key=lambda kv: -kv[1]):
     out.append(f"| `{n}` | {t / max(step_n[n],1):.1f} | {100 * t / tot:.1f} % |")
 (REPO / "profiles" / f"{tag}_launches.md").write_text("\n".join(out) + "\n")
 
-# ---- full capture
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-r = list(csv.reader(raw.splitlines()))
-hdr, units, data = r[0], r[1], r[2:]
-idx = {h: i for i, h in enumerate(hdr)}
+# ---- full capture(s)
 want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
         ("lts__t_bytes.sum", "L2 bytes"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
         ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
-        ("smsp__inst_executed.sum", "warp inst")]
+        ("smsp__inst_executed.sum", "warp inst"), ("smsp__inst_executed_pipe_fma.sum", "FMA-pipe inst"),
+        ("smsp__inst_executed_pipe_fp64.sum", "FP64-pipe inst"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %")]
 def num(x):
     try: return float(x.replace(",", ""))
     except ValueError: return float("nan")
@@ -65,19 +63,26 @@ def to_bytes(v, u):
 lines = [f"# {tag}: ncu --set full captures (`--clock-control none --import-source on`)\n",
          "| kernel | " + " | ".join(w[1] for w in want) + " |", "|---|" + "---:|" * len(want)]
 traffic = collections.defaultdict(list)
-for d in data:
-    name = short(d[idx["Kernel Name"]])
-    cells = []
-    for m, _ in want:
-        if m in idx:
-            v, u = num(d[idx[m]]), units[idx[m]]
-            cells.append(f"{v:,.1f} {u}" if u not in ("",) else f"{v:,.0f}")
-        else:
-            cells.append("-")
-    lines.append(f"| `{name}` | " + " | ".join(cells) + " |")
-    rd = to_bytes(num(d[idx["dram__bytes_read.sum"]]), units[idx["dram__bytes_read.sum"]])
-    wr = to_bytes(num(d[idx["dram__bytes_write.sum"]]), units[idx["dram__bytes_write.sum"]])
-    traffic[name.split("<")[0]].append(rd + wr)
+rows_all = []
+for one in rep.split(","):
+    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(raw.splitlines()))
+    hdr, units, data = r[0], r[1], r[2:]
+    rows_all.append(({h: i for i, h in enumerate(hdr)}, units, data))
+for idx, units, data in rows_all:
+  for d in data:
+      name = short(d[idx["Kernel Name"]])
+      cells = []
+      for m, _ in want:
+          if m in idx:
+              v, u = num(d[idx[m]]), units[idx[m]]
+              cells.append(f"{v:,.1f} {u}" if u not in ("",) else f"{v:,.0f}")
+          else:
+              cells.append("-")
+      lines.append(f"| `{name}` | " + " | ".join(cells) + " |")
+      rd = to_bytes(num(d[idx["dram__bytes_read.sum"]]), units[idx["dram__bytes_read.sum"]])
+      wr = to_bytes(num(d[idx["dram__bytes_write.sum"]]), units[idx["dram__bytes_write.sum"]])
+      traffic[name.split("<")[0]].append(rd + wr)
 (REPO / "profiles" / f"{tag}_kernels.md").write_text("\n".join(lines) + "\n")
 tj = {k: float(sorted(v)[len(v) // 2]) for k, v in traffic.items()}
 tj["_note"] = "median dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (caches flushed before each launch)"
