@@ -314,8 +314,8 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     SICP_REQUIRE(value >= 0 && value <= 256, SICP_ERR_BAD_ARG, "rs_blocks out of range");
     c.rs_blocks = (int)value;
   } else if (k == "match_group") {
-    SICP_REQUIRE(value == 0 || value == 1 || value == 4 || value == 8 || value == 16, SICP_ERR_BAD_ARG,
-                 "match_group must be 0 (auto), 1, 4, 8 or 16");
+    SICP_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16, SICP_ERR_BAD_ARG,
+                 "match_group must be 0 (auto), 1, 2, 4, 8 or 16");
     c.match_group = (int)value;
   } else if (k == "host_sync_every") {
     SICP_REQUIRE(value >= 1 && value <= 1024, SICP_ERR_BAD_ARG, "host_sync_every out of range");

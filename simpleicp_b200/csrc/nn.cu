@@ -306,15 +306,17 @@ __device__ __forceinline__ void match_coop_body(
       const double fxl = fmax(qx - (g.ox + cx * g.h), 0.0), fxh = fmax((g.ox + (cx + 1) * g.h) - qx, 0.0);
       const double fyl = fmax(qy - (g.oy + cy * g.h), 0.0), fyh = fmax((g.oy + (cy + 1) * g.h) - qy, 0.0);
       const double fzl = fmax(qz - (g.oz + cz * g.h), 0.0), fzh = fmax((g.oz + (cz + 1) * g.h) - qz, 0.0);
-      {
-        const int x = cx - 1 + sub;
-        bool own = sub < 3 && x >= 0 && x < g.nx;
+#pragma unroll
+      for (int t = sub; t < 3 || t == sub; t += MG) {  // one pass for MG >= 4, two for MG = 2
+        const int x = cx - 1 + t;
+        bool own = t < 3 && x >= 0 && x < g.nx;
         // with a warm-start bound the two side cells of the own row are usually out of reach
-        const double bx = (sub == 0) ? fxl : ((sub == 2) ? fxh : 0.0);
+        const double bx = (t == 0) ? fxl : ((t == 2) ? fxh : 0.0);
         if (bx * bx > best * (1.0 + 1e-12)) own = false;
         const long long row0 = ((long long)cz * g.ny + cy) * g.nx;
         const uint32_t os = own ? cs[row0 + x] : 0u, oe = own ? cs[row0 + x + 1] : 0u;
         scan_range(g.recs, os, oe, qx, qy, qz, best, bidx, bpos);
+        if (MG >= 3) break;
       }
 #pragma unroll
       for (int o = MG / 2; o > 0; o >>= 1) {
@@ -914,7 +916,8 @@ void batch_match_launch(Ctx& c, Batch& b, bool warm) {
   int mg = c.match_group;
   if (mg == 0 || mg == 1) mg = (total <= 16384) ? 16 : ((total <= 65536) ? 8 : 4);
   const dim3 grid((unsigned)((b.Kmax * mg + 127) / 128), b.n_pairs);
-  if (mg == 4) k_match_batch<4><<<grid, 128, 0, c.stream>>>(a);
+  if (mg == 2) k_match_batch<2><<<grid, 128, 0, c.stream>>>(a);
+  else if (mg == 4) k_match_batch<4><<<grid, 128, 0, c.stream>>>(a);
   else if (mg == 8) k_match_batch<8><<<grid, 128, 0, c.stream>>>(a);
   else k_match_batch<16><<<grid, 128, 0, c.stream>>>(a);
   SICP_CUDA(cudaGetLastError());
@@ -970,7 +973,8 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
                                                     c.q_nrm.p, c.mov_xyz.p, K, rmax,          \
                                                     with_distance ? 1 : 0, c.nn_idx.p, out,   \
                                                     c.unresolved.p, lh, cap2, co)
-    if (mg == 4) SICP_LAUNCH_COOP(4);
+    if (mg == 2) SICP_LAUNCH_COOP(2);
+    else if (mg == 4) SICP_LAUNCH_COOP(4);
     else if (mg == 8) SICP_LAUNCH_COOP(8);
     else SICP_LAUNCH_COOP(16);
 #undef SICP_LAUNCH_COOP

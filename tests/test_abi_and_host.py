@@ -224,6 +224,24 @@ def fake_register(Xf, Xm, **kw):
 table = batch.simpleicp_batch(lambda i: (np.full((1, 3), float(i)), np.zeros((1, 3))), n, rank=rank,
                               world_size=world, dist=dist, register_fn=fake_register)
 assert calls == batch.shard_pairs(n, world, rank), calls
+# a pair that cannot be registered fails ALONE: its rank still joins the collective, every rank gets
+# the full table and the same BatchError
+class TooFew(Exception):
+    code = 3
+def flaky(Xf, Xm, **kw):
+    if int(Xf[0, 0]) == 4:
+        raise TooFew("Too few correspondences! ...")
+    return R(int(Xf[0, 0]))
+try:
+    batch.simpleicp_batch(lambda i: (np.full((1, 3), float(i)), np.zeros((1, 3))), n, rank=rank,
+                          world_size=world, dist=dist, register_fn=flaky)
+    raise SystemExit("BatchError expected")
+except batch.BatchError as e:
+    assert e.failed.tolist() == [4] and e.table.shape == (n, 20) and np.isnan(e.table[4, :16]).all()
+    assert e.table[4, 16] == -3 and np.array_equal(e.table[5, :16].reshape(4, 4), np.eye(4) * 6)
+t2 = batch.simpleicp_batch(lambda i: (np.full((1, 3), float(i)), np.zeros((1, 3))), n, rank=rank,
+                           world_size=world, dist=dist, register_fn=flaky, on_error="nan")
+assert t2[4, 16] == -3 and t2[3, 16] == 5
 for i in range(n):
     assert np.array_equal(table[i, :16].reshape(4, 4), np.eye(4) * (i + 1))
     assert table[i, 16] == i + 2 and table[i, 17] == 100 + i and table[i, 18] == 0.5 * i and table[i, 19] == 0.25 * i

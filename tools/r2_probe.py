@@ -48,6 +48,15 @@ def c3():
         lsq = e.lsq_params(np.zeros(6), np.zeros(6), np.zeros(6), 1.0)
         p = e.run_params(0.3, 1.0, 100, lsq)
         show("C3", stages(e, p))
+        e.set_option("fused", 1); e.set_option("warm_start", 1); e.set_option("sphere_scan", 1)
+        for mg in (2, 4, 8):
+            e.set_option("match_group", mg)
+            e.iterate(p, x_in=np.zeros(6), want_record=True)
+            for _ in range(12):
+                e.iterate(p, want_record=True)
+            sc, sw = e.time_stages(p, 20, True), e.time_stages(p, 20, False)
+            print(f"C3 match_group={mg}: match cold {sc['match_grid']*1e3:.1f} warm {sw['match_grid']*1e3:.1f} us")
+        e.set_option("match_group", 0)
         import torch
 
         for fused in (0, 1):

@@ -1,6 +1,6 @@
 """Turn the ncu outputs in gpurun_out/ into the tracked summaries under profiles/.
 
-    python tools/summarize_profiles.py <launch_list.csv> <full_capture.ncu-rep>[,<more.ncu-rep>...] <tag>
+    python tools/summarize_profiles.py <launch_list.csv> <capture.ncu-rep | capture_raw.csv>[,<more>...] <tag>
 
 Writes profiles/<tag>_launches.md (per-kernel totals and shares of the step), profiles/<tag>_kernels.md
 (key metrics of every captured launch) and profiles/ncu_traffic.json (DRAM bytes per launch of
@@ -65,8 +65,10 @@ lines = [f"# {tag}: ncu --set full captures (`--clock-control none --import-sour
 traffic = collections.defaultdict(list)
 rows_all = []
 for one in rep.split(","):
-    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    r = list(csv.reader(raw.splitlines()))
+    # a .ncu-rep (converted here) or the raw CSV page already written on the GPU box
+    raw = (open(one).read() if one.endswith(".csv") else
+           subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
+    r = list(csv.reader([ln for ln in raw.splitlines() if ln.startswith('"')]))
     hdr, units, data = r[0], r[1], r[2:]
     rows_all.append(({h: i for i, h in enumerate(hdr)}, units, data))
 for idx, units, data in rows_all:
