@@ -79,6 +79,7 @@ static void register_batch(Ctx& c, int n_pairs, const double* const* fix_xyz, co
     mo[(size_t)i + 1] = mo[(size_t)i] + n_mov[i];
     Kmax = std::max<long long>(Kmax, std::min<long long>(rp->correspondences, n_fix[i]));
   }
+  Kmax = (Kmax + 1) & ~1ll;  // even: every pair's slice of the per-query arrays starts 16-byte aligned
   b.total_fix = fo[(size_t)n_pairs];
   b.total_mov = mo[(size_t)n_pairs];
   b.Kmax = Kmax;

@@ -1355,8 +1355,17 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
 constexpr int RSF_NACC = 30;             // accumulators per role
 constexpr int RSF_NPART = 3 * RSF_NACC;  // partial sums per block
 
+constexpr int RSF_TILE = 768;  // correspondences per TMA-staged tile of the moment pass
+
 struct SharedF {
   Shared s;
+  // the block's share of (normal, distance, matched point), staged by 1-D TMA bulk copies that are
+  // issued at kernel entry: the moment pass does not depend on the select, only the keep test
+  // does, so the data crosses L2/HBM while the block works out median and MAD
+  alignas(16) float4 t_nrm[RSF_TILE];
+  alignas(16) double t_dist[RSF_TILE];
+  alignas(16) double t_xyz[3 * RSF_TILE];
+  alignas(8) uint64_t t_bar;
   double redf[RS_WARPS][RSF_NACC];
   double totf[RSF_NPART];
   double m1[13];  // sum phi
@@ -1562,6 +1571,27 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
   if (st->stop) return;  // a previous iteration met the stop rule (or asked for a re-run)
   RSF_STAMP(0);
 
+  // ---- this block's share; its first tile starts moving now (even tile starts keep every source
+  // address 16-byte aligned; a last odd tile reads 8 bytes of slack the buffers are allocated with)
+  const long long chunk = (((K + G - 1) / G) + 1) & ~1ll;
+  const long long i0 = min((long long)bid * chunk, K), i1 = min(i0 + chunk, K);
+  auto issue_tile = [&](long long t0) {
+    const uint32_t nt = (uint32_t)min((long long)RSF_TILE, i1 - t0);
+    const uint32_t b_n = nt * 16u, b_d = (nt * 8u + 15u) & ~15u, b_p = (nt * 24u + 15u) & ~15u;
+    mbar_expect_tx(&sf.t_bar, b_n + b_d + b_p);
+    tma_load_1d(sf.t_nrm, a.q_nrm + t0, b_n, &sf.t_bar);
+    tma_load_1d(sf.t_dist, a.dist + t0, b_d, &sf.t_bar);
+    tma_load_1d(sf.t_xyz, a.m_xyz + 3 * t0, b_p, &sf.t_bar);
+  };
+  if (tid == 0) {
+    mbar_init(&sf.t_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool have_tile = i0 < i1;
+  if (tid == 0 && have_tile) issue_tile(i0);
+  uint32_t tile_phase = 0;
+
   // ---- select (every block, identical result)
   unsigned int n1 = 0;
   double median = 0.0, mad = 0.0;
@@ -1594,11 +1624,6 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
     double acc[RSF_NACC];
 #pragma unroll
     for (int j = 0; j < RSF_NACC; ++j) acc[j] = 0.0;
-    const long long chunk = (K + G - 1) / G;
-    const long long i0 = bid * chunk, i1 = min(i0 + chunk, K);
-    const float4* __restrict__ qn = a.q_nrm;
-    const double* __restrict__ dd = a.dist;
-    const double* __restrict__ mv = a.m_xyz;
     auto accumulate = [&](const float4 nr, const double d, const double p0, const double p1,
                           const double p2, const double f0, const double f1, const double f2) {
       const double u0 = p0 - cm[0], u1 = p1 - cm[1], u2 = p2 - cm[2];
@@ -1641,22 +1666,22 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
         acc[24] += sc;
       }
     };
-    // everything is streamed (no index chase): two elements per trip, all loads up front
-    for (long long i = i0 + sub; i < i1; i += 256) {
-      const long long ib = i + 128;
-      const bool hb = ib < i1;
-      const long long jb = hb ? ib : i;
-      const float4 nrA = qn[i], nrB = qn[jb];
-      const double dA = dd[i], dB = dd[jb];
-      const double pA0 = mv[3 * i + 0], pA1 = mv[3 * i + 1], pA2 = mv[3 * i + 2];
-      const double pB0 = mv[3 * jb + 0], pB1 = mv[3 * jb + 1], pB2 = mv[3 * jb + 2];
-      const bool kA = ((double)nrA.w >= a.min_planarity) && (fabs(dA - median) <= lim);
-      const bool kB = hb && ((double)nrB.w >= a.min_planarity) && (fabs(dB - median) <= lim);
-      if (kA) accumulate(nrA, dA, pA0, pA1, pA2, 0.0, 0.0, 0.0);
-      if (kB) accumulate(nrB, dB, pB0, pB1, pB2, 0.0, 0.0, 0.0);
-      if (role == 0) {
-        a.keep[i] = kA ? 1 : 0;
-        if (hb) a.keep[ib] = kB ? 1 : 0;
+    // tiles of RSF_TILE correspondences from shared memory (the first one has been in flight since
+    // kernel entry; K <= 113 000 has a single tile per block)
+    for (long long t0 = i0; t0 < i1; t0 += RSF_TILE) {
+      const int nt = (int)min((long long)RSF_TILE, i1 - t0);
+      mbar_wait(&sf.t_bar, tile_phase);
+      tile_phase ^= 1u;
+      for (int e = sub; e < nt; e += 128) {
+        const float4 nr = sf.t_nrm[e];
+        const double d = sf.t_dist[e];
+        const bool kp = ((double)nr.w >= a.min_planarity) && (fabs(d - median) <= lim);
+        if (kp) accumulate(nr, d, sf.t_xyz[3 * e + 0], sf.t_xyz[3 * e + 1], sf.t_xyz[3 * e + 2], 0.0, 0.0, 0.0);
+        if (role == 0) a.keep[t0 + e] = kp ? 1 : 0;
+      }
+      if (t0 + RSF_TILE < i1) {
+        __syncthreads();  // everybody is done with the tile before it is overwritten
+        if (tid == 0) issue_tile(t0 + RSF_TILE);
       }
     }
 #pragma unroll
@@ -1671,6 +1696,8 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
       for (int ww = r; ww < RS_WARPS; ww += 3) vv += sf.redf[ww][j];
       wk.partials[(size_t)tid * G + bid] = vv;
     }
+  } else if (have_tile) {
+    mbar_wait(&sf.t_bar, tile_phase);  // never leave with a bulk copy into this block's shared memory in flight
   }
   RSF_STAMP(3);
 
