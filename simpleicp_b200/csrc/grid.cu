@@ -426,13 +426,19 @@ __global__ void __launch_bounds__(256) k_cell_count_batch(const CloudPlan* __res
                                                           unsigned int* __restrict__ occ) {
   const CloudPlan pl = plans[blockIdx.y];
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= pl.n) return;
-  const int cx = cell_coord(pl.xyz[3 * i + 0], pl.ox, pl.inv_h, pl.nx);
-  const int cy = cell_coord(pl.xyz[3 * i + 1], pl.oy, pl.inv_h, pl.ny);
-  const int cz = cell_coord(pl.xyz[3 * i + 2], pl.oz, pl.inv_h, pl.nz);
-  const uint32_t cell = (uint32_t)(((long long)cz * pl.ny + cy) * pl.nx + cx);
-  cid[pl.rec_base + i] = cell;
-  if (atomicAdd(&count[pl.cell_base + cell], 1u) == 0u) atomicAdd(&occ[blockIdx.y], 1u);
+  int first = 0;
+  if (i < pl.n) {
+    const int cx = cell_coord(pl.xyz[3 * i + 0], pl.ox, pl.inv_h, pl.nx);
+    const int cy = cell_coord(pl.xyz[3 * i + 1], pl.oy, pl.inv_h, pl.ny);
+    const int cz = cell_coord(pl.xyz[3 * i + 2], pl.oz, pl.inv_h, pl.nz);
+    const uint32_t cell = (uint32_t)(((long long)cz * pl.ny + cy) * pl.nx + cx);
+    cid[pl.rec_base + i] = cell;
+    first = (atomicAdd(&count[pl.cell_base + cell], 1u) == 0u) ? 1 : 0;
+  }
+  // occupied cells of this cloud: ONE atomic per block (one per first touch serialised 30 000
+  // same-address atomics per cloud: 113 us for 1.6 M points, ncu r2)
+  const int n_first = __syncthreads_count(first);
+  if (threadIdx.x == 0 && n_first) atomicAdd(&occ[blockIdx.y], (unsigned int)n_first);
 }
 
 __global__ void __launch_bounds__(256) k_scatter_batch(const CloudPlan* __restrict__ plans,

@@ -75,6 +75,7 @@ struct Shared {
   unsigned long long stamp[2];
   // in-block refinement of the selected radix bin
   unsigned int h256[256];
+  unsigned int rank_acc[RS_THREADS];  // rank_select: partial ranks per candidate
   unsigned long long small[64];
   unsigned long long sel_above;
   unsigned int small_n;
@@ -1374,33 +1375,32 @@ struct SharedF {
 
 // Plan + gather + selection; true on success (median, mad, n1 set; n1 == 0 is a success).
 // k-th smallest (0-based) and its successor among n <= RS_THREADS keys in shared memory by direct
-// ranking: one candidate per thread, n broadcast reads — two block barriers instead of the eight
-// radix passes block_select() needs when the keys share their leading bytes (they always do here:
-// the candidates come from a handful of adjacent histogram bins).
+// ranking — three block barriers instead of the eight radix passes block_select() needs when the
+// keys share their leading bytes (they always do here: the candidates come from a handful of
+// adjacent histogram bins).
 __device__ __forceinline__ void rank_select(Shared& s, const unsigned long long* keys, int n, unsigned int k,
                                             unsigned long long& klo, unsigned long long& khi) {
-  // RS_THREADS / n threads share one candidate (each compares it with a slice of the list)
+  // work item = (candidate, quarter of the list): n * 4 items over the block's threads, the four
+  // partial ranks of a candidate meet in a shared-memory counter
+  constexpr int PARTS = 4;
   const int tid = threadIdx.x;
-  const int parts = max(1, min(RS_THREADS / max(n, 1), 8));
-  const int c = tid / parts, part = tid - c * parts;
-  if (tid < 256) s.h256[tid] = 0;
-  // (parts > 1 implies n <= RS_THREADS / 2 = 192 < 256 slots)
+  for (int c = tid; c < n; c += RS_THREADS) s.rank_acc[c] = 0;
   __syncthreads();
-  unsigned int r = 0;
-  unsigned long long key = 0;
-  if (c < n) {
-    key = keys[c];
-    for (int j = part; j < n; j += parts) {
+  for (int w = tid; w < n * PARTS; w += RS_THREADS) {
+    const int c = w / PARTS, part = w - c * PARTS;
+    const unsigned long long key = keys[c];
+    unsigned int r = 0;
+    for (int j = part; j < n; j += PARTS) {
       const unsigned long long kj = keys[j];
       r += (kj < key || (kj == key && j < c)) ? 1u : 0u;
     }
-    if (parts > 1) atomicAdd(&s.h256[c], r);
+    atomicAdd(&s.rank_acc[c], r);
   }
   __syncthreads();
-  if (c < n && part == 0) {
-    const unsigned int rank = (parts > 1) ? s.h256[c] : r;
-    if (rank == k) s.small[0] = key;
-    if (rank == k + 1u) s.small[1] = key;
+  for (int c = tid; c < n; c += RS_THREADS) {
+    const unsigned int rank = s.rank_acc[c];
+    if (rank == k) s.small[0] = keys[c];
+    if (rank == k + 1u) s.small[1] = keys[c];
   }
   __syncthreads();
   klo = s.small[0];

@@ -27,23 +27,24 @@ for r in rows:
 agg = collections.OrderedDict()
 for n, us in seq:
     a = agg.setdefault(n, [0, 0.0, 1e30, 0.0]); a[0] += 1; a[1] += us; a[2] = min(a[2], us); a[3] = max(a[3], us)
-# steady-state step = last (match, [bf, bf_finalize], reject_solve) groups
-steady = [(n, us) for n, us in seq if n.startswith(("k_match_grid", "k_reject_solve", "k_rs_fused", "k_bf_"))]
-tail = steady[-40:]
-step_us = collections.defaultdict(float); step_n = collections.Counter()
-for n, us in tail:
-    step_us[n] += us; step_n[n] += 1
-n_steps = max(step_n.get("k_rs_fused", 0) or step_n.get("k_reject_solve<1>", 0) or max(step_n.values()), 1)
+# steady-state step: median duration of the last launches of each loop kernel (the timed region of
+# bench.py ends the capture; medians ignore the few first-iteration / re-run launches among them)
+import statistics
+loop = [(n, us) for n, us in seq if n.startswith(("k_match_grid", "k_reject_solve", "k_rs_fused", "k_bf_"))]
+last = collections.defaultdict(list)
+for n, us in loop[-120:]:
+    last[n].append(us)
+step_us = {n: statistics.median(v) for n, v in last.items() if len(v) >= 5}
 tot = sum(step_us.values())
 out = [f"# {tag}: ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold caches, serialised)\n",
-       "Command: `python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1` under ncu; absolute times are",
+       "Command: `python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-c4c5` under ncu (first 600 launches); absolute times are",
        "cold-cache and serialised, the SHARES are what is comparable with the CUDA-event numbers of bench.py.\n",
        "## All launches by kernel\n", "| kernel | launches | total us | min us | max us |", "|---|---:|---:|---:|---:|"]
 for n, (c, t, mn, mx) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| `{n}` | {c} | {t:.1f} | {mn:.1f} | {mx:.1f} |")
-out += ["\n## Steady-state iteration (last launches of the timed region)\n", "| kernel | us per iteration | share |", "|---|---:|---:|"]
+out += ["\n## Steady-state iteration (last launches of the timed region)\n", "| kernel | median us per launch | share |", "|---|---:|---:|"]
 for n, t in sorted(step_us.items(), key=lambda kv: -kv[1]):
-    out.append(f"| `{n}` | {t / max(step_n[n],1):.1f} | {100 * t / tot:.1f} % |")
+    out.append(f"| `{n}` | {t:.1f} | {100 * t / tot:.1f} % |")
 (REPO / "profiles" / f"{tag}_launches.md").write_text("\n".join(out) + "\n")
 
 # ---- full capture(s)
