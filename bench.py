@@ -189,7 +189,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "setup_s": {"normals": results[0][2], "total": max(totals), "wall": wall},
-    }))
+    }), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -280,6 +280,11 @@ def run_c5(sb, rank, world, local, dist, pairs_per_gpu, n_pts):
             "api": "simpleicp_b200.simpleicp_batch(pairs, engine='batched') on pinned host arrays, records all-gathered"}
 
 
+def _trace(msg):
+    if os.environ.get("SICP_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} t={time.time() % 1000:.1f}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -289,6 +294,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
 
+    _trace("numa bound, importing package")
     import simpleicp_b200 as sb
     from simpleicp_b200 import _capi, batch
 
@@ -298,6 +304,7 @@ def run_b200(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _trace("process group ready")
     K, n = args.correspondences, args.points
 
     X_fix, X_mov, H_true = make_pair(n, rank)
@@ -305,6 +312,7 @@ def run_b200(args):
     Xm_pin = torch.from_numpy(X_mov).pin_memory()
     out_pin = torch.empty((n, 3), dtype=torch.float64).pin_memory()
 
+    _trace("inputs pinned")
     sampler = ClockSampler(local) if rank == 0 else None
     eng = _capi.Engine(local)
 
@@ -322,6 +330,7 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    _trace("setup done")
     # ---- warm-up: a real registration's worth of iterations brings the loop to its steady state
     # (the state every iteration after the first few of a registration is in), then the timed
     # region (cold L2 before every step)
@@ -343,6 +352,7 @@ def run_b200(args):
     rec = eng.iterate(params, want_record=True)
     n_kept = int(rec.n_kept)
 
+    _trace("cold timing done")
     # ---- same loop, warm L2, iterations queued back to back with no host sync (what sicp_run does)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -363,6 +373,7 @@ def run_b200(args):
         torch.cuda.synchronize()
     t_load1 = time.time()
 
+    _trace("clock window done")
     # ---- end to end through the public API on pinned host arrays
     def one_e2e():
         return sb.register(Xf_pin.numpy(), Xm_pin.numpy(), correspondences=K, engine=eng,
@@ -397,6 +408,7 @@ def run_b200(args):
     e2e_value = K * its_total / e2e_s_max
     dH_true = float(np.linalg.norm(res.H - H_true))
 
+    _trace("e2e done")
     # ---- the north-star API as a user calls it: pageable arrays, no engine argument; and the class
     extra = {}
     if world == 1:
@@ -448,6 +460,7 @@ def run_b200(args):
             "H_frobenius_vs_H_true": float(np.linalg.norm(rl.T - H_true)),
             "api": "simpleicp_b200.simpleicp_linearized(X_fix, X_mov, correspondences=K, engine=<reused>)"}}
 
+    _trace("variants done")
     # ---- BASELINE configs[3] and [4] through their public entry points (all ranks take part)
     c4 = c5 = None
     if not args.no_c4c5:
@@ -465,7 +478,10 @@ def run_b200(args):
         except Exception as e:  # noqa: BLE001 — the headline line must not depend on the side configs
             c5 = c5 or {"error": repr(e)}
 
+    _trace("c4/c5 done")
     if rank != 0:
+        eng.close()
+        batch.close_engine_pool()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -556,7 +572,10 @@ def run_b200(args):
         "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "variants": variants,
         "c4": c4, "c5": c5,
     }
-    print(json.dumps(line))
+    # flushed at once: the line must not sit in a pipe buffer while the process tears CUDA / NCCL down
+    print(json.dumps(line), flush=True)
+    eng.close()
+    batch.close_engine_pool()
     if world > 1:
         dist.destroy_process_group()
 
