@@ -300,9 +300,9 @@ def run_b200(args):
 
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: whatever NCCL logs (version banner, INFO lines when
+        # the caller asks for them) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _trace("process group ready")
     K, n = args.correspondences, args.points
