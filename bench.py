@@ -303,6 +303,9 @@ def run_b200(args):
         # stdout carries exactly one JSON line: whatever NCCL logs (version banner, INFO lines when
         # the caller asks for them) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (this image exports NCCL_DEBUG=VERSION, whose banner ignores NCCL_DEBUG_FILE; WARN has none)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _trace("process group ready")
     K, n = args.correspondences, args.points
@@ -339,11 +342,17 @@ def run_b200(args):
         rec = eng.iterate(params, want_record=True)
     launches0 = eng.timings()["kernel_launches"]
     barrier()
-    st = eng.time_stages(params, args.steps, True)
+    # the K timed steps: one CUDA-event pair around each whole iteration (cold L2 before each)
+    st_outer = eng.time_stages(params, args.steps, True, outer_only=True)
     barrier()
     launches = eng.timings()["kernel_launches"] - launches0
+    # the per-kernel split of the same step, from a second set of steps with events between the
+    # kernels (those events cost a few microseconds of stream bubbles, hence not in `value`)
+    st = eng.time_stages(params, args.steps, True)
+    st["iteration_with_inner_events"] = st["iteration"]
+    st["iteration"] = st_outer["iteration"]
     path = eng.phase_times()[28]
-    total_ms = st["iteration"] * args.steps
+    total_ms = st_outer["iteration"] * args.steps
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

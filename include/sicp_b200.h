@@ -268,8 +268,10 @@ int32_t sicp_get_timings(sicp_ctx* ctx, sicp_timings* t /*[h]*/);
 /* Measurement hook: run `reps` iterations from the current device state and return the average
  * device time (CUDA events on the context's stream) of each kernel group, in milliseconds:
  * ms[0] grid match kernel, ms[1] brute-force pass (launched, usually empty), ms[2] reject+solve
- * kernel, ms[3] whole iteration.  flush_l2 != 0 overwrites a 256 MiB scratch buffer before every
- * iteration (outside the timed intervals) so each one starts with a cold L2.                    */
+ * kernel, ms[3] whole iteration.  flush_l2 bit 0: overwrite a 256 MiB scratch buffer before every
+ * iteration (outside the timed intervals) so each one starts with a cold L2; bit 1: record only
+ * the two outer events (ms[0..2] = 0) — the inner events cost several microseconds of stream
+ * bubbles per iteration, so the whole-iteration time is taken without them.                     */
 int32_t sicp_time_stages(sicp_ctx* ctx, const sicp_run_params* p, int32_t reps, int32_t flush_l2,
                          double ms[4] /*[h]*/);
 /* Diagnostics: %globaltimer stamps block 0 took in the last reject+solve kernel, microseconds

@@ -485,10 +485,12 @@ class Engine:
         self._check(self._lib.sicp_transform(self._h, _d16(H), _ptr(out)))
         return out
 
-    def time_stages(self, params: RunParams, reps: int, flush_l2: bool) -> dict:
-        """Average device milliseconds per iteration of each kernel group (CUDA events)."""
+    def time_stages(self, params: RunParams, reps: int, flush_l2: bool, outer_only: bool = False) -> dict:
+        """Average device milliseconds per iteration of each kernel group (CUDA events).
+        outer_only: only the events around the whole iteration (no bubbles from the inner ones)."""
         ms = (C.c_double * 4)()
-        self._check(self._lib.sicp_time_stages(self._h, C.byref(params), int(reps), int(flush_l2), ms))
+        self._check(self._lib.sicp_time_stages(self._h, C.byref(params), int(reps),
+                                               (1 if flush_l2 else 0) | (2 if outer_only else 0), ms))
         return {"match_grid": ms[0], "bruteforce_pass": ms[1], "reject_solve": ms[2], "iteration": ms[3]}
 
     def phase_times(self) -> list:

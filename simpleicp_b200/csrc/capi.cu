@@ -946,6 +946,11 @@ int32_t sicp_time_stages(sicp_ctx* ctx, const sicp_run_params* p, int32_t reps, 
   require_normals(c);
   SICP_REQUIRE(p && ms && reps >= 1, SICP_ERR_BAD_ARG, "bad argument");
   const size_t kFlushBytes = 256ull << 20;
+  // flush_l2: bit 0 = overwrite the 256 MiB scratch before every iteration; bit 1 = record only the
+  // two outer events (the three inner ones cost ~8 us of stream bubbles per iteration: the
+  // whole-iteration time is taken without them, the per-kernel split in a second call with them)
+  const bool outer_only = (flush_l2 & 2) != 0;
+  flush_l2 &= 1;
   if (flush_l2) c.flush_buf.reserve(kFlushBytes);
   cudaEvent_t e[4];
   for (auto& ev : e) SICP_CUDA(cudaEventCreate(&ev));
@@ -956,14 +961,17 @@ int32_t sicp_time_stages(sicp_ctx* ctx, const sicp_run_params* p, int32_t reps, 
     for (int r = 0; r < reps; ++r) {
       if (flush_l2) SICP_CUDA(cudaMemsetAsync(c.flush_buf.p, r & 0xff, kFlushBytes, c.stream));
       SICP_CUDA(cudaEventRecord(e[0], c.stream));
-      launch_iteration(c, *p, ctx->it_counter, false, 0, allow_fused, false, e[1], e[2]);
+      launch_iteration(c, *p, ctx->it_counter, false, 0, allow_fused, false, outer_only ? nullptr : e[1],
+                       outer_only ? nullptr : e[2]);
       SICP_CUDA(cudaEventRecord(e[3], c.stream));
       SICP_CUDA(cudaEventSynchronize(e[3]));
       ctx->it_counter++;
       float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
-      cudaEventElapsedTime(&t01, e[0], e[1]);
-      cudaEventElapsedTime(&t12, e[1], e[2]);
-      cudaEventElapsedTime(&t23, e[2], e[3]);
+      if (!outer_only) {
+        cudaEventElapsedTime(&t01, e[0], e[1]);
+        cudaEventElapsedTime(&t12, e[1], e[2]);
+        cudaEventElapsedTime(&t23, e[2], e[3]);
+      }
       cudaEventElapsedTime(&t03, e[0], e[3]);
       acc[0] += t01;
       acc[1] += t12;
