@@ -126,6 +126,8 @@ def normals_probe():
 
 if __name__ == "__main__":
     normals_probe()
+    if len(sys.argv) > 1 and sys.argv[1] == "normals":
+        sys.exit(0)
     c3()
     small("dragon", {})
     small("bunny", {"max_overlap_distance": 1.0})

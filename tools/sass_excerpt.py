@@ -17,6 +17,7 @@ out = ["# SASS evidence (round 2): `cuobjdump -sass simpleicp_b200/libsicp_b200.
 keep = ("k_bf_nn", "k_match_grid_coop", "k_match_batch", "k_rs_fused", "k_rs_batch", "k_reject_solve", "k_knn",
         "k_pca", "k_transform", "k_match_grid")
 bf = None
+rsf = None
 for f in funcs[1:]:
     name = f.split("\n", 1)[0].strip()
     dem = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
@@ -32,7 +33,11 @@ for f in funcs[1:]:
                f"{cnt(r'SHFL')} | {cnt(r'\b(LDL|STL)\b')} |")
     if short.startswith("k_bf_nn"):
         bf = [ln for ln in lines if re.search(r"UBLKCP|SYNCS|FENCE|MBAR", ln)]
+    if short == "k_rs_fused":
+        rsf = [ln for ln in lines if re.search(r"UBLKCP|SYNCS|FENCE", ln)]
 out += ["", "## `k_bf_nn`: the TMA / mbarrier instructions", "", "```"]
 out += [re.sub(r"\s+/\* 0x[0-9a-f]+ \*/", "", ln).rstrip() for ln in (bf or [])][:40] + ["```", ""]
+out += ["## `k_rs_fused`: the three bulk copies that stage a block's share of the moment pass", "", "```"]
+out += [re.sub(r"\s+/\* 0x[0-9a-f]+ \*/", "", ln).rstrip() for ln in (rsf or [])][:20] + ["```", ""]
 (REPO / "profiles" / "r2_sass.md").write_text("\n".join(out))
 print("\n".join(out))
