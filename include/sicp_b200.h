@@ -115,6 +115,21 @@ int32_t sicp_estimate_normals(sicp_ctx* ctx, int32_t neighbors, float* nx, float
 /* The reference's "columns already present" hook (simpleicp.py:176-178).                       */
 int32_t sicp_set_normals(sicp_ctx* ctx, const float* nx, const float* ny, const float* nz,
                          const float* planarity /*[h|d] K each*/);
+/* Movable-side attributes (optional; the default run has none).  Arrays of n_mov floats in the
+ * movable cloud's own frame, NaN where not estimated; all four NULL clears them; a new movable
+ * cloud (sicp_set_clouds / sicp_register) clears them too.
+ *  - planarity: second branch of CorrPts.reject_wrt_planarity (corrpts.py:157-162): when pc_mov
+ *    carries a planarity column, a correspondence must pass min_planarity on BOTH sides; NaN
+ *    fails.  The median / MAD of the distance rejection are taken over that set.
+ *  - max_angle_rad in [0, pi/2]: CorrPts.reject_wrt_to_angle_between_normals — the hook the
+ *    reference declares, calls after the distance rejection (simpleicp.py:207, commented out)
+ *    and leaves `raise NotImplementedError` (corrpts.py:190-193).  Here: a correspondence that
+ *    survived both rejections is dropped when acos|n_fix . (R n_mov)| > max_angle_rad, R the
+ *    rotation of the iteration's transform.  Negative: no angle test.
+ * Both act in sicp_match/sicp_reject/sicp_solve, sicp_iterate and sicp_run; sicp_register and
+ * sicp_register_batch take their clouds themselves and always run without them.               */
+int32_t sicp_set_mov_normals(sicp_ctx* ctx, const float* nx, const float* ny, const float* nz,
+                             const float* planarity /*[h|d] n_mov each*/, double max_angle_rad);
 /* neighbour indices of the last sicp_estimate_normals (test/inspection hook), K x neighbors; they
  * are only kept when option "keep_knn" was 1 during that call.                                  */
 int32_t sicp_get_knn(sicp_ctx* ctx, int64_t* idx /*[h|d] K x k*/, double* dist2 /*[h|d] or NULL*/);

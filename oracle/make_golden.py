@@ -65,6 +65,9 @@ CONFIGS = {
             "rbp_observation_weights": (50.0, 50.0, 0.0, 20.0, np.inf, 0.0),
         },
     ),
+    # pc_mov carries normal columns (pc_mov.estimate_normals before run): the second branch of
+    # CorrPts.reject_wrt_planarity (corrpts.py:157-162), which none of the reference tests reaches
+    "dragon_movnormals": ("dragon1.xyz", "dragon2.xyz", {"_mov_normals": 10}),
 }
 TRAVEL = ("dragon", "bunny", "multisensor", "webots")  # inputs committed as fixtures
 TRAVEL_LARGE = ("airborne", "terrestrial")  # > 1M points each: delta + byte-plane + LZMA (see below)
@@ -225,6 +228,17 @@ def capture(name, file1, file2, kwargs):
         orig_inrange(self, X, max_range)
         rec["idx_overlap"] = self.idx_selected.astype(np.int32)
 
+    kwargs = dict(kwargs)
+    mov_neighbors = kwargs.pop("_mov_normals", None)
+    pc_mov_pre = None
+    if mov_neighbors:
+        # all movable points are selected by default: normals for every one of them, in pc_mov's own frame
+        pc_mov_pre = PointCloud(X_mov, columns=["x", "y", "z"], copy=True)
+        pc_mov_pre.estimate_normals(mov_neighbors)
+        rec["mov_normals"] = np.column_stack(
+            [pc_mov_pre[c].to_numpy() for c in ("nx", "ny", "nz")]).astype(np.float32)
+        rec["mov_planarity"] = pc_mov_pre["planarity"].to_numpy().astype(np.float32)
+
     corrpts.CorrPts.match = match
     corrpts.CorrPts.reject_wrt_point_to_plane_distances = rej
     optimization.SimpleICPOptimization.estimate_parameters = est
@@ -232,7 +246,7 @@ def capture(name, file1, file2, kwargs):
     pointcloud.PointCloud.select_in_range = inrange
     try:
         pc_fix = PointCloud(X_fix, columns=["x", "y", "z"])
-        pc_mov = PointCloud(X_mov, columns=["x", "y", "z"], copy=True)
+        pc_mov = pc_mov_pre if pc_mov_pre is not None else PointCloud(X_mov, columns=["x", "y", "z"], copy=True)
         icp = SimpleICP(verbose=False)
         icp.add_point_clouds(pc_fix, pc_mov)
         t = time.time()
@@ -273,6 +287,8 @@ def capture(name, file1, file2, kwargs):
     )
     if "idx_overlap" in rec:
         out["idx_overlap"] = rec["idx_overlap"]
+    if "mov_normals" in rec:
+        out["mov_normals"], out["mov_planarity"] = rec["mov_normals"], rec["mov_planarity"]
     kw = {k: v for k, v in kwargs.items()}
     out["kwargs_repr"] = np.array(repr(kw))
     np.savez_compressed(GOLD / f"ref_{name}.npz", **out)

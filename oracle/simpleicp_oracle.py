@@ -141,14 +141,25 @@ def match(
 
 
 def reject(
-    d: np.ndarray, planarity_f32: np.ndarray, min_planarity: float
+    d: np.ndarray, planarity_f32: np.ndarray, min_planarity: float,
+    mov_planarity_f32: Optional[np.ndarray] = None,
+    angle_ok: Optional[np.ndarray] = None,
 ) -> Tuple[np.ndarray, float, float]:
     """corrpts.py:139-163 then 165-188 — planarity mask first (float32 values compared in float64, NaN -> drop),
     then |d - median| <= 3 * MAD on the survivors with MAD *unscaled* (SciPy default scale=1.0;
-    corrpts.py:186).  Returns (keep mask over K, median, mad)."""
+    corrpts.py:186).  Returns (keep mask over K, median, mad).
+
+    ``mov_planarity_f32`` (K values: the planarity of each correspondence's movable point) is
+    the second branch of reject_wrt_planarity (corrpts.py:157-162), taken when pc_mov carries
+    a planarity column.  ``angle_ok`` (K booleans) is NOT reference behaviour — the reference's
+    reject_wrt_to_angle_between_normals raises NotImplementedError (corrpts.py:190-193); it is
+    applied where the reference would call it: after the distance rejection (simpleicp.py:207)."""
     # corrpts.py:152-155 compares `Sparse[float32].to_numpy() >= min_planarity`; pandas hands the
     # sparse float32 column back as float64, so the comparison is a float64 one.
     keep1 = planarity_f32.astype(np.float64) >= min_planarity
+    if mov_planarity_f32 is not None:  # corrpts.py:157-162
+        with np.errstate(invalid="ignore"):
+            keep1 = keep1 & (mov_planarity_f32.astype(np.float64) >= min_planarity)
     ds = d[keep1]
     if ds.size == 0:
         return np.zeros_like(keep1), np.nan, np.nan
@@ -157,7 +168,20 @@ def reject(
     keep2 = np.abs(ds - median) <= 3 * mad
     keep = np.zeros_like(keep1)
     keep[np.flatnonzero(keep1)[keep2]] = True
+    if angle_ok is not None:
+        keep &= angle_ok
     return keep, float(median), float(mad)
+
+
+def angle_between_normals_ok(normals_f32: np.ndarray, mov_normals_f32: np.ndarray, H: np.ndarray,
+                             max_angle_deg: float) -> np.ndarray:
+    """Extension (no reference behaviour, see ``reject``): |n_fix . (R n_mov)| >= cos(max angle),
+    R the rotation of the transform the movable cloud is matched under; normals are axes, so the
+    angle is taken modulo their sign; NaN normals fail."""
+    rn = mov_normals_f32.astype(np.float64) @ H[:3, :3].T
+    with np.errstate(invalid="ignore"):
+        c = np.abs(np.sum(rn * normals_f32.astype(np.float64), axis=1))
+        return c >= (0.0 if max_angle_deg >= 90.0 else np.cos(np.deg2rad(max_angle_deg)))
 
 
 # --------------------------------------------------------------------------- optimization.py
@@ -309,6 +333,8 @@ def simpleicp(
     normals: Optional[Tuple[np.ndarray, np.ndarray]] = None,
     trace: Optional[Trace] = None,
     static_tree: bool = False,
+    mov_normals: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+    max_angle_between_normals: Optional[float] = None,
 ):
     """SimpleICP.run (simpleicp.py:75-324), restated without pandas.
 
@@ -316,7 +342,9 @@ def simpleicp(
     "columns nx, ny, nz, planarity already present" hook (simpleicp.py:176-178).
     ``static_tree=True`` is NOT the reference algorithm: it builds the kd-tree once and moves
     the queries by inv(H) (the product's strategy); it exists so tests can show the two are
-    equivalent.  Returns (H, X_mov_transformed, x[6], sigma[6], residuals).
+    equivalent.  ``mov_normals=(normals_f32[n_mov,3], planarity_f32[n_mov])`` stands for a pc_mov
+    that carries normal columns (corrpts.py:157-162); ``max_angle_between_normals`` is the
+    extension described in ``reject``.  Returns (H, X_mov_transformed, x[6], sigma[6], residuals).
     """
     X_fix = np.ascontiguousarray(X_fix, dtype=float)
     X2 = np.array(X_mov, dtype=float, copy=True)  # the reference mutates pc2 in place
@@ -388,7 +416,12 @@ def simpleicp(
             X2 = transform_by_H(X2, H)  # :188
             idx_nn, d = match(X_fix, idx_sel, nrm, X2)  # :201
             X2 = transform_by_H(X2, np.linalg.inv(H))  # :202
-        keep, med, mad = reject(d, plan, min_planarity)  # :205-206
+        mov_plan = angle_ok = None
+        if mov_normals is not None:
+            mov_plan = mov_normals[1][idx_nn]
+            if max_angle_between_normals is not None:
+                angle_ok = angle_between_normals_ok(nrm, mov_normals[0][idx_nn], H, max_angle_between_normals)
+        keep, med, mad = reject(d, plan, min_planarity, mov_plan, angle_ok)  # :205-206
         n_corr = int(keep.sum())
         if n_corr < 6:  # :209-214
             raise OracleICPError(

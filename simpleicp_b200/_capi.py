@@ -25,7 +25,7 @@ SIGN_DGEEV, SIGN_CANONICAL = 0, 1
 SYMBOLS = (
     "sicp_abi_version", "sicp_create", "sicp_destroy", "sicp_last_error", "sicp_set_option",
     "sicp_set_clouds", "sicp_set_selected", "sicp_select_in_range", "sicp_estimate_normals",
-    "sicp_set_normals", "sicp_get_knn", "sicp_match", "sicp_reject", "sicp_solve",
+    "sicp_set_normals", "sicp_set_mov_normals", "sicp_get_knn", "sicp_match", "sicp_reject", "sicp_solve",
     "sicp_uncertainties", "sicp_run", "sicp_get_transform", "sicp_get_residuals", "sicp_iterate", "sicp_transform",
     "sicp_select_n_points", "sicp_register",
     "sicp_register_batch", "sicp_get_timings", "sicp_time_stages", "sicp_get_phase_times",
@@ -130,6 +130,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "sicp_select_in_range": [vp, C.POINTER(dbl), dbl, vp, C.POINTER(i64)],
         "sicp_estimate_normals": [vp, i32, vp, vp, vp, vp],
         "sicp_set_normals": [vp, vp, vp, vp, vp],
+        "sicp_set_mov_normals": [vp, vp, vp, vp, vp, C.c_double],
         "sicp_get_knn": [vp, vp, vp],
         "sicp_match": [vp, C.POINTER(dbl), vp, vp],
         "sicp_reject": [vp, dbl, vp, C.POINTER(i64), C.POINTER(dbl)],
@@ -350,6 +351,20 @@ class Engine:
             if v.size != self.K:
                 raise ValueError("normal arrays must have one entry per selected point")
         self._check(self._lib.sicp_set_normals(self._h, *[_ptr(v) for v in a]))
+
+    def set_mov_normals(self, nx, ny, nz, planarity, max_angle_deg=None):
+        """Movable-side attributes (sicp_set_mov_normals): n_mov floats each, NaN = not estimated;
+        ``set_mov_normals(None, None, None, None)`` clears them.  ``max_angle_deg`` switches the
+        rejection by the angle between the normals on (degrees, like the facade's other angles)."""
+        if nx is None and ny is None and nz is None and planarity is None:
+            self._check(self._lib.sicp_set_mov_normals(self._h, None, None, None, None, -1.0))
+            return
+        a = [np.ascontiguousarray(v, dtype=np.float32) for v in (nx, ny, nz, planarity)]
+        for v in a:
+            if v.size != self.n_mov:
+                raise ValueError("movable normal arrays must have one entry per movable point")
+        ang = -1.0 if max_angle_deg is None else float(np.deg2rad(max_angle_deg))
+        self._check(self._lib.sicp_set_mov_normals(self._h, *[_ptr(v) for v in a], ang))
 
     def get_knn(self, k: int):
         """Neighbour lists of the last estimate_normals (needs set_option("keep_knn", 1) before it)."""

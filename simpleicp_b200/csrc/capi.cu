@@ -388,6 +388,7 @@ int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, con
   SICP_CUDA(cudaStreamSynchronize(c.copy_stream));  // the caller may reuse fix_xyz after return
   c.K = 0;
   c.have_normals = false;
+  c.mov_attr = false;
   c.nn_pos_valid = false;
   c.matched = c.rejected = c.solved = false;
   API_END
@@ -459,6 +460,35 @@ int32_t sicp_set_normals(sicp_ctx* ctx, const float* nx, const float* ny, const 
   c.q_nrm.reserve(c.K);
   k_join_f4<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(s, c.K, c.q_nrm.p);
   c.have_normals = true;
+  sync(c);
+  API_END
+}
+
+int32_t sicp_set_mov_normals(sicp_ctx* ctx, const float* nx, const float* ny, const float* nz,
+                             const float* planarity, double max_angle_rad) {
+  API_BEGIN(ctx)
+  SICP_REQUIRE(c.n_mov > 0, SICP_ERR_STATE, "no clouds: call sicp_set_clouds first");
+  if (!nx && !ny && !nz && !planarity) {  // back to the default run
+    c.mov_attr = false;
+    c.mov_cos_max = -1.0;
+    c.matched = c.rejected = c.solved = false;
+    return SICP_OK;
+  }
+  SICP_REQUIRE(nx && ny && nz && planarity, SICP_ERR_BAD_ARG, "NULL normal array");
+  SICP_REQUIRE(!(max_angle_rad > 1.5707963267948966), SICP_ERR_BAD_ARG,
+               "max_angle_rad must be <= pi/2 (normals are axes), or negative for no angle test");
+  c.stage.reserve(sizeof(float) * 4 * c.n_mov);
+  float* s = reinterpret_cast<float*>(c.stage.p);
+  copy_any(c, s, nx, sizeof(float) * c.n_mov);
+  copy_any(c, s + c.n_mov, ny, sizeof(float) * c.n_mov);
+  copy_any(c, s + 2 * c.n_mov, nz, sizeof(float) * c.n_mov);
+  copy_any(c, s + 3 * c.n_mov, planarity, sizeof(float) * c.n_mov);
+  c.mov_nrm.reserve(c.n_mov);
+  k_join_f4<<<(unsigned)((c.n_mov + 255) / 256), 256, 0, c.stream>>>(s, c.n_mov, c.mov_nrm.p);
+  SICP_CUDA(cudaGetLastError());
+  c.mov_attr = true;
+  c.mov_cos_max = (max_angle_rad >= 0.0) ? (max_angle_rad >= 1.5707963267948966 ? 0.0 : cos(max_angle_rad)) : -1.0;
+  c.matched = c.rejected = c.solved = false;
   sync(c);
   API_END
 }
@@ -828,6 +858,7 @@ int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, const
   c.gfix.built = false;
   c.K = 0;
   c.have_normals = false;
+  c.mov_attr = false;
   c.nn_pos_valid = false;
   c.matched = c.rejected = c.solved = false;
   // Transfers in the order the pipeline consumes them.  The fixed cloud goes first on the

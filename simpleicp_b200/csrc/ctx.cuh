@@ -81,6 +81,11 @@ struct Ctx {
   DevBuf<double> q_xyz;   // K x 3 gathered fixed points
   DevBuf<float4> q_nrm;   // (nx, ny, nz, planarity) float32 as the reference stores them
   bool have_normals = false;
+  // movable-side attributes (sicp_set_mov_normals): per movable point, in its own frame
+  DevBuf<float4> mov_nrm;
+  DevBuf<float4> q_nrm_eff;  // K: fixed normal + effective planarity of the current match (nn.cu: effective_planarity)
+  bool mov_attr = false;
+  double mov_cos_max = -1.0; // cos(max angle between normals); < 0 = no angle test
   int knn_k = 0;
   DevBuf<long long> knn_idx;
   DevBuf<double> knn_d2;
@@ -145,6 +150,13 @@ struct Ctx {
 
   Batch* batch = nullptr;  // created by the first sicp_register_batch
 };
+// what the match kernels / reject kernels see of the movable-side attributes
+inline const float4* mov_attr_nrm(Ctx& c) { return c.mov_attr ? c.mov_nrm.p : nullptr; }
+inline float4* mov_attr_eff(Ctx& c) {
+  if (!c.mov_attr) return nullptr;
+  c.q_nrm_eff.reserve(c.K > 0 ? c.K : 1);
+  return c.q_nrm_eff.p;
+}
 
 // ---- batched engine: many small pairs per launch (BASELINE configs[4]) ----
 // One descriptor per pair, resident in device memory; every batched kernel takes the pair from

@@ -161,7 +161,39 @@ struct CorrOut {
   uint32_t* nn_pos;
   int warm;              // nn_pos holds positions of the previous iteration
   int sphere;            // finish a search inside the sphere of the first known point (option "sphere_scan")
+  // Movable-side attributes (null = the reference's default run, pc_mov without normals):
+  // mov_nrm[j] = (nx, ny, nz, planarity) of movable point j in ITS OWN frame, NaN where not
+  // estimated.  q_eff[i] receives the fixed normal with an "effective planarity" that carries
+  // both movable-side tests to the reject kernels (effective_planarity below).
+  const float4* mov_nrm;
+  float4* q_eff;
+  double cos_max;        // cos of the largest accepted angle between the normals; < 0: no angle test
 };
+// CorrPts.reject_wrt_planarity's second branch (corrpts.py:157-162: a correspondence also needs
+// planarity >= min_planarity on the MOVABLE side when pc_mov carries the column; NaN, i.e. "not
+// estimated", fails the comparison) and the hook the reference leaves unimplemented
+// (reject_wrt_to_angle_between_normals, corrpts.py:190-193; called after the distance rejection,
+// simpleicp.py:207).  Both are folded into one float per correspondence:
+//   |w| = min(planarity_fix, planarity_mov)   (NaN if either is NaN): both planarity tests are
+//         |w| >= min_planarity, and the median / MAD population is the set that passes them;
+//   sign(w) = 1 if the angle between the fixed normal and the ROTATED movable normal exceeds the
+//         limit (normals are axes: the angle is taken modulo their sign): such a correspondence
+//         takes part in the median / MAD like in the reference's call order, and is dropped after it.
+__device__ __forceinline__ float effective_planarity(const CorrOut& co, const Rigid& T, long long qi,
+                                                     long long midx, const float4& nr) {
+  if (co.mov_nrm == nullptr) return nr.w;
+  const float4 m = co.mov_nrm[midx];
+  float w = (m.w >= nr.w) ? nr.w : ((m.w < nr.w) ? m.w : __int_as_float(0x7fc00000));
+  if (co.cos_max >= 0.0) {
+    const double rx = T.r[0] * (double)m.x + T.r[1] * (double)m.y + T.r[2] * (double)m.z;
+    const double ry = T.r[3] * (double)m.x + T.r[4] * (double)m.y + T.r[5] * (double)m.z;
+    const double rz = T.r[6] * (double)m.x + T.r[7] * (double)m.y + T.r[8] * (double)m.z;
+    const double c = fabs(rx * (double)nr.x + ry * (double)nr.y + rz * (double)nr.z);
+    if (!(c >= co.cos_max)) w = __int_as_float(__float_as_int(w) | 0x80000000);
+  }
+  co.q_eff[qi] = make_float4(nr.x, nr.y, nr.z, w);
+  return fabsf(w);
+}
 __device__ __forceinline__ void store_matched(const CorrOut& co, long long qi, double x, double y, double z) {
   if (co.m_xyz) {
     co.m_xyz[3 * qi + 0] = x;
@@ -195,7 +227,7 @@ __global__ void __launch_bounds__(128)
     const float4 nr = q_nrm[i];
     const double d = plane_distance(st->T, mov_xyz, bidx, px, py, pz, nr);
     out[i] = d;
-    lin_hist_add(st, lin_hist, nr.w, d, co.binstore, co.bin_cap, i);
+    lin_hist_add(st, lin_hist, effective_planarity(co, st->T, i, bidx, nr), d, co.binstore, co.bin_cap, i);
     store_matched(co, i, mov_xyz[3 * bidx + 0], mov_xyz[3 * bidx + 1], mov_xyz[3 * bidx + 2]);
   } else {
     out[i] = best;
@@ -465,7 +497,7 @@ __device__ __forceinline__ void match_coop_body(
     const Rec m = g.recs[bpos];
     const double d = plane_distance_rec(st->T, m, px, py, pz, nr);
     out[qi] = d;
-    lin_hist_add(st, lin_hist, nr.w, d, co.binstore, co.bin_cap, qi);
+    lin_hist_add(st, lin_hist, effective_planarity(co, st->T, qi, bidx, nr), d, co.binstore, co.bin_cap, qi);
     store_matched(co, qi, m.x, m.y, m.z);
   } else {
     out[qi] = best;
@@ -506,7 +538,8 @@ __global__ void __launch_bounds__(128) k_match_batch(BatchMatchArgs a) {
   const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (gt / MG >= pd.K) return;
   const long long q = pd.q_off;
-  const CorrOut co{a.binstore + (size_t)blockIdx.y * LH_BINS * a.bin_cap, a.bin_cap, a.m_xyz + 3 * q, a.nn_pos + q, a.warm, a.sphere};
+  const CorrOut co{a.binstore + (size_t)blockIdx.y * LH_BINS * a.bin_cap, a.bin_cap, a.m_xyz + 3 * q, a.nn_pos + q, a.warm, a.sphere,
+                   nullptr, nullptr, -1.0};
   match_coop_body<MG>(pd.gmov, a.state + blockIdx.y, a.q_xyz + 3 * q, a.q_nrm + q, nullptr, pd.K, 1 << 30, 1,
                       a.nn_idx + q, a.dist + q, nullptr, a.lin_hist + (size_t)blockIdx.y * (LH_BINS + 2), -1.0,
                       co, gt);
@@ -740,7 +773,7 @@ __global__ void __launch_bounds__(128)
     const float4 nr = q_nrm[q];
     const double dd = plane_distance(T, mov_xyz, ix, q_xyz[3 * q + 0], q_xyz[3 * q + 1], q_xyz[3 * q + 2], nr);
     out[q] = dd;
-    lin_hist_add(st, lin_hist, nr.w, dd, co.binstore, co.bin_cap, q);
+    lin_hist_add(st, lin_hist, effective_planarity(co, T, q, ix, nr), dd, co.binstore, co.bin_cap, q);
     store_matched(co, q, mov_xyz[3 * ix + 0], mov_xyz[3 * ix + 1], mov_xyz[3 * ix + 2]);
   } else {
     out[q] = d;
@@ -821,7 +854,8 @@ static void bf_launch(Ctx& c, bool with_distance, double* out, bool whole_set) {
   k_bf_finalize<<<(unsigned)((q_total + 127) / 128), 128, 0, c.stream>>>(
       partials, n_chunks, q_total, qlist, qcount, c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p,
       with_distance ? 1 : 0, c.nn_idx.p, out, with_distance ? c.lin_hist.p : nullptr,
-      with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, nullptr, 0, 0} : CorrOut{nullptr, 0, nullptr, nullptr, 0, 0});
+      with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, nullptr, 0, 0, mov_attr_nrm(c), mov_attr_eff(c), c.mov_cos_max}
+                    : CorrOut{nullptr, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, -1.0});
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 2;
 }
@@ -904,8 +938,9 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
   c.m_xyz.reserve(3 * std::max<long long>(K, 1));
   c.nn_pos.reserve(std::max<long long>(K, 1));
   const bool warm = with_distance && c.warm_start && c.nn_pos_valid && c.nn_pos_K == K;
-  const CorrOut co = with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, c.nn_pos.p, warm ? 1 : 0, c.sphere_scan}
-                                   : CorrOut{nullptr, 0, nullptr, nullptr, 0, 0};
+  const CorrOut co = with_distance ? CorrOut{c.binstore.p, c.bin_cap, c.m_xyz.p, c.nn_pos.p, warm ? 1 : 0, c.sphere_scan,
+                                             mov_attr_nrm(c), mov_attr_eff(c), c.mov_cos_max}
+                                   : CorrOut{nullptr, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, -1.0};
   if (with_distance) {
     c.nn_pos_valid = (c.nn_engine != SICP_NN_BRUTE) && c.match_group != 1;
     c.nn_pos_K = K;

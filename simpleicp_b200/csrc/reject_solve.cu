@@ -286,7 +286,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
     __syncthreads();
     for (long long i = bid * (long long)RS_THREADS + threadIdx.x; i < K;
          i += (long long)G * RS_THREADS) {
-      if ((double)a.q_nrm[i].w >= minpl) {
+      if (pl_stat(a.q_nrm[i].w, a.pl_signed) >= minpl) {
         const double v = (SEL == 0) ? a.dist[i] : fabs(a.dist[i] - center);
         const unsigned long long key = f64_to_key(v);
         if (level == 0 || (key >> kShift[level - 1]) == prefix)
@@ -338,7 +338,7 @@ __device__ void radix_median(Shared& s, const RSArgs& a, RSWork wk, double cente
   }
   for (long long i = bid * (long long)RS_THREADS + threadIdx.x; i < K;
        i += (long long)G * RS_THREADS) {
-    if ((double)a.q_nrm[i].w >= minpl) {
+    if (pl_stat(a.q_nrm[i].w, a.pl_signed) >= minpl) {
       const double v = (SEL == 0) ? a.dist[i] : fabs(a.dist[i] - center);
       const unsigned long long key = f64_to_key(v);
       const unsigned long long top = key >> shift;
@@ -891,7 +891,7 @@ __device__ bool predicted_median_mad(Shared& s, const RSArgs& a, RSWork wk, cons
   unsigned long long* cand_med = wk.cand;
   unsigned long long* cand_edge = wk.cand + RS_CAP;
   for (long long i = blockIdx.x * (long long)RS_THREADS + tid; i < a.K; i += (long long)gridDim.x * RS_THREADS) {
-    if ((double)a.q_nrm[i].w >= a.stat_minpl) {
+    if (pl_stat(a.q_nrm[i].w, a.pl_signed) >= a.stat_minpl) {
       const double d = a.dist[i];
       const int b = lh_bin(d, pm, pd);
       if (b < LH_BINS) {
@@ -1045,8 +1045,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
       const float4 nrA = qn[i];
       const float4 nrB = hb ? qn[ib] : make_float4(0.f, 0.f, 0.f, -1.f);
       const double dA = dd[i], dB = hb ? dd[ib] : 0.0;
-      const bool kA = ((double)nrA.w >= a.min_planarity) && (fabs(dA - median) <= lim);
-      const bool kB = hb && ((double)nrB.w >= a.min_planarity) && (fabs(dB - median) <= lim);
+      const bool kA = pl_keep(nrA.w, a.min_planarity, a.pl_signed) && (fabs(dA - median) <= lim);
+      const bool kB = hb && pl_keep(nrB.w, a.min_planarity, a.pl_signed) && (fabs(dB - median) <= lim);
       const long long jA = kA ? nn[i] : 0, jB = kB ? nn[ib] : 0;
       const long long ia = kA ? i : i0, ibb = kB ? ib : i0;
       const double pA0 = mv[3 * jA + 0], pA1 = mv[3 * jA + 1], pA2 = mv[3 * jA + 2];
@@ -1675,7 +1675,7 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
       for (int e = sub; e < nt; e += 128) {
         const float4 nr = sf.t_nrm[e];
         const double d = sf.t_dist[e];
-        const bool kp = ((double)nr.w >= a.min_planarity) && (fabs(d - median) <= lim);
+        const bool kp = pl_keep(nr.w, a.min_planarity, a.pl_signed) && (fabs(d - median) <= lim);
         if (kp) accumulate(nr, d, sf.t_xyz[3 * e + 0], sf.t_xyz[3 * e + 1], sf.t_xyz[3 * e + 2], 0.0, 0.0, 0.0);
         if (role == 0) a.keep[t0 + e] = kp ? 1 : 0;
       }
@@ -2195,7 +2195,8 @@ void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve
   RSArgs a;
   a.K = K;
   a.dist = c.dist.p;
-  a.q_nrm = c.q_nrm.p;
+  a.q_nrm = c.mov_attr ? c.q_nrm_eff.p : c.q_nrm.p;
+  a.pl_signed = c.mov_attr ? 1 : 0;
   a.q_xyz = c.q_xyz.p;
   a.nn_idx = c.nn_idx.p;
   a.mov_xyz = c.mov_xyz.p;
@@ -2276,7 +2277,8 @@ void rs_fused_launch(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, in
   RSArgs a;
   a.K = K;
   a.dist = c.dist.p;
-  a.q_nrm = c.q_nrm.p;
+  a.q_nrm = c.mov_attr ? c.q_nrm_eff.p : c.q_nrm.p;
+  a.pl_signed = c.mov_attr ? 1 : 0;
   a.q_xyz = c.q_xyz.p;
   a.nn_idx = c.nn_idx.p;
   a.mov_xyz = c.mov_xyz.p;
@@ -2324,6 +2326,7 @@ void batch_rs_launch(Ctx& c, Batch& b, const sicp_run_params& p, int it, bool wa
   a = RSArgs{};
   a.dist = b.dist.p;
   a.q_nrm = b.q_nrm.p;
+  a.pl_signed = 0;
   a.q_xyz = b.q_xyz.p;
   a.keep = b.keep.p;
   a.binstore = b.binstore.p;

@@ -82,7 +82,16 @@ struct RSArgs {
   int bin_cap;
   const double* m_xyz;         // matched movable point (caller coordinates), K x 3
   int want_sigma;              // evaluate the parameter sigmas even if the stop rule does not fire
+  // q_nrm is the match kernel's per-iteration copy whose .w is the signed effective planarity
+  // (nn.cu: effective_planarity): |w| enters both planarity tests, a set sign bit = rejected by
+  // the angle between the normals after the distance rejection
+  int pl_signed;
 };
+__device__ __forceinline__ double pl_stat(float w, int pl_signed) { return (double)(pl_signed ? fabsf(w) : w); }
+__device__ __forceinline__ bool pl_keep(float w, double min_planarity, int pl_signed) {
+  if (pl_signed) return (double)fabsf(w) >= min_planarity && !signbit(w);
+  return (double)w >= min_planarity;
+}
 
 struct RSWork {
   unsigned int* hist;

@@ -161,14 +161,32 @@ def register(
     stepwise: bool = False,
     on_normals=None,
     want_normals: bool = True,
+    mov_normals: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = None,
+    max_angle_between_normals: Optional[float] = None,
 ) -> _Result:
     """Core of both front ends: one registration on one GPU.
 
     ``idx_selected`` restricts the candidate fixed points (the reference's ``selected`` column),
     ``normals=(nx, ny, nz, planarity)`` are full-length (n_fix) arrays supplied instead of being
     estimated (the reference's pre-computed-columns hook, simpleicp.py:176-178).
+
+    ``mov_normals=(nx, ny, nz, planarity)``: full-length (n_mov) attributes of the movable cloud
+    in its own frame, NaN where not estimated.  With them a correspondence must also pass
+    ``min_planarity`` on the movable side — what the reference does when ``pc_mov`` carries a
+    planarity column (corrpts.py:157-162).  ``max_angle_between_normals`` (degrees, needs
+    ``mov_normals``) additionally drops correspondences whose normals differ by more than that
+    angle after the distance rejection: the reference declares this step
+    (``reject_wrt_to_angle_between_normals``, simpleicp.py:207) but leaves it unimplemented.
     """
     _check_arguments(distance_weights, rbp_observed_values, rbp_observation_weights)
+    if max_angle_between_normals is not None:
+        if mov_normals is None:
+            raise SimpleICPException(
+                "max_angle_between_normals needs the normals of the movable point cloud "
+                "(PointCloud.estimate_normals on pc_mov, or mov_normals=...)."
+            )
+        if not 0.0 <= float(max_angle_between_normals) <= 90.0:
+            raise SimpleICPException("max_angle_between_normals must be within [0, 90] degrees.")
     if debug_dirpath:
         _log.info(f'Write debug files to directory "{debug_dirpath}"')
         Path(debug_dirpath).mkdir(parents=True, exist_ok=True)
@@ -180,7 +198,7 @@ def register(
     )
     eng = engine if engine is not None else default_engine()
     fused = (idx_selected is None and normals is None and not stepwise and on_normals is None
-             and not want_normals)
+             and not want_normals and mov_normals is None)
     try:  # noqa: PLR1702
         if fused:
             # the whole of SimpleICP.run as one library call: nothing but the clouds goes in,
@@ -190,6 +208,8 @@ def register(
                                    obs, w_obs, rbp_observation_weights, transform_out)
         eng.set_clouds(X_fix, X_mov)
         n_fix = eng.n_fix
+        if mov_normals is not None:
+            eng.set_mov_normals(*mov_normals, max_angle_deg=max_angle_between_normals)
         idx = None if idx_selected is None else np.asarray(idx_selected, dtype=np.int64)
 
         if np.isfinite(max_overlap_distance):
@@ -436,11 +456,18 @@ class SimpleICP:
         rbp_observed_values: Tuple[float] = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0),
         rbp_observation_weights: Tuple[float] = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0),
         debug_dirpath: str = "",
+        max_angle_between_normals: Optional[float] = None,
     ) -> Tuple[np.ndarray, np.ndarray, optimization.RigidBodyParameters, np.ndarray]:
         """Run the registration.  Arguments, units (degrees for the observed angles), return
         tuple ``(H, X_mov_transformed, rbp, distance_residuals)`` and side effects (pc_mov
         transformed in place; pc_fix gains nx, ny, nz, planarity and a thinned ``selected``
-        column) are those of the reference's ``SimpleICP.run``."""
+        column) are those of the reference's ``SimpleICP.run``.
+
+        If ``pc_mov`` carries normal columns (``pc_mov.estimate_normals(k)`` was called before),
+        correspondences are also rejected by the planarity of the movable point, as in the
+        reference (corrpts.py:157-162).  ``max_angle_between_normals`` (degrees; one keyword more
+        than the reference, default off) enables the rejection step the reference only declares
+        (``CorrPts.reject_wrt_to_angle_between_normals``)."""
         start_time = time.time()
         pc1, pc2 = self.pc1, self.pc2
         sel = pc1["selected"].to_numpy(dtype=bool)
@@ -457,6 +484,12 @@ class SimpleICP:
         X2 = pc2.X
         sel2 = pc2["selected"].to_numpy(dtype=bool)
         X2_search = X2 if sel2.all() else np.ascontiguousarray(X2[sel2])
+        mov_normals = None
+        if "planarity" in pc2.columns:
+            cols = [c if c in pc2.columns else None for c in _NORMAL_COLUMNS]
+            mov_normals = tuple(
+                (np.asarray(pc2[c].to_numpy(), dtype=np.float32) if c is not None
+                 else np.full(len(sel2), np.nan, dtype=np.float32))[sel2] for c in cols)
 
         res = register(
             pc1.X, X2_search, correspondences=correspondences, neighbors=neighbors,
@@ -464,6 +497,7 @@ class SimpleICP:
             min_change=min_change, max_iterations=max_iterations, distance_weights=distance_weights,
             rbp_observed_values=rbp_observed_values, rbp_observation_weights=rbp_observation_weights,
             debug_dirpath=debug_dirpath, idx_selected=idx0, normals=normals, on_normals=store_normals,
+            mov_normals=mov_normals, max_angle_between_normals=max_angle_between_normals,
         )
         pc1.idx_selected = res.idx_selected
         if sel2.all():

@@ -11,7 +11,7 @@ GOLD = REPO / "tests" / "golden"
 REFERENCE = Path("/root/reference")
 
 TRAVEL = ("dragon", "bunny", "multisensor", "webots")
-ALIAS = {"dragon_observed": "dragon"}
+ALIAS = {"dragon_observed": "dragon", "dragon_movnormals": "dragon"}
 
 
 def pytest_configure(config):

@@ -279,3 +279,13 @@ def test_synthetic_generators_equal_the_oracles():
     src = (REPO / "bench.py").read_text()
     b200_arm = src[src.index("def run_b200"):src.index("# ---- CPU baseline beside it")]
     assert "oracle" not in b200_arm  # only the cpu_baseline / parity legs of bench.py touch oracle/
+
+
+def test_angle_rejection_needs_movable_normals():
+    """Argument check of the facade happens before any device work."""
+    import simpleicp_b200 as sb
+    X = np.random.default_rng(0).random((50, 3))
+    with pytest.raises(sb.SimpleICPException, match="needs the normals of the movable"):
+        sb.simpleicp(X, X, max_angle_between_normals=10.0)
+    with pytest.raises(sb.SimpleICPException, match=r"within \[0, 90\]"):
+        sb.simpleicp(X, X, mov_normals=(X[:, 0],) * 4, max_angle_between_normals=120.0)

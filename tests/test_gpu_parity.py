@@ -852,3 +852,111 @@ def test_barrier_free_kernel_many_tiles_per_block(gpu):
     np.testing.assert_allclose(a.H, b.H, rtol=0, atol=1e-11)
     np.testing.assert_allclose(a.residuals, b.residuals, rtol=0, atol=1e-11)
     assert np.linalg.norm(a.H - H_true) < 2e-2
+
+
+# ---- movable-side attributes: pc_mov with normal columns (corrpts.py:157-162) and the rejection
+# ---- by the angle between normals the reference declares but leaves unimplemented (:190-193)
+def _mov_attr(g):
+    return tuple(np.ascontiguousarray(g["mov_normals"][:, a]) for a in range(3)) + (g["mov_planarity"],)
+
+
+def test_movable_side_planarity_lockstep(gpu):
+    """Reference run with pc_mov.estimate_normals() called first (golden dragon_movnormals,
+    captured from the unmodified reference): the keep mask of the first iteration is bit-identical
+    stage by stage, and the whole run has the reference's iteration and kept counts and its H."""
+    g = load_golden("dragon_movnormals")
+    X_fix, X_mov = load_pair("dragon_movnormals")
+    nrm = full_normals(g, X_fix.shape[0])
+    with _capi.Engine() as e:
+        e.set_clouds(X_fix, X_mov)
+        e.set_mov_normals(*_mov_attr(g))
+        e.set_selected(g["idx_sel"])
+        e.set_normals(*[a[g["idx_sel"]] for a in nrm])
+        idx_nn, d = e.match(np.eye(4))
+        assert np.array_equal(idx_nn, g["it_pc2_idx"][0])
+        keep, n_kept, _ = e.reject(0.3)
+        assert n_kept == int(g["it_keep"][0].sum())
+        assert np.array_equal(keep.astype(bool), g["it_keep"][0])
+        # clearing the attributes gives the plain dragon mask again
+        e.set_mov_normals(None, None, None, None)
+        e.match(np.eye(4))
+        keep0 = e.reject(0.3)[0]
+        assert np.array_equal(keep0.astype(bool), load_golden("dragon")["it_keep"][0])
+    for fused in (1, 0):
+        with _capi.Engine() as e:
+            e.set_option("fused", fused)
+            res = sb.register(X_fix, X_mov, normals=nrm, mov_normals=_mov_attr(g), engine=e)
+        kept = [r["n_kept"] for r in res.records]
+        ref_kept = [int(k.sum()) for k in g["it_keep"]]
+        dH = np.linalg.norm(res.H - g["H"])
+        print(f"movable planarity (fused={fused}): |dH|_F = {dH:.3e}, kept {kept} vs {ref_kept}")
+        assert kept == ref_kept
+        assert res.iterations == len(ref_kept)
+        assert dH < 1e-9
+        np.testing.assert_allclose(res.residuals, g["residuals"], rtol=0, atol=1e-9)
+
+
+def test_movable_side_normals_through_the_class(gpu):
+    """The reference's user-level route: pc_mov.estimate_normals(k) then SimpleICP.run — all
+    100 000 movable normals estimated on the GPU (compared with the reference's), then used."""
+    g = load_golden("dragon_movnormals")
+    X_fix, X_mov = load_pair("dragon_movnormals")
+    pc_fix, pc_mov = sb.PointCloud(X_fix, columns=["x", "y", "z"]), sb.PointCloud(X_mov, columns=["x", "y", "z"])
+    pc_mov.estimate_normals(10)
+    pl = pc_mov["planarity"].to_numpy().astype(np.float32)
+    n_gpu = np.column_stack([pc_mov[c].to_numpy() for c in ("nx", "ny", "nz")]).astype(np.float32)
+    np.testing.assert_allclose(pl, g["mov_planarity"], rtol=0, atol=2e-5)
+    dots = np.abs(np.sum(n_gpu.astype(np.float64) * g["mov_normals"].astype(np.float64), axis=1))
+    ok = g["mov_planarity"] > 0.05
+    assert dots[ok].min() > 1 - 1e-6
+    exact = (n_gpu == g["mov_normals"]).all(axis=1).mean()
+    print(f"movable normals: bit-identical float32 rows {exact:.4f}, planarity max diff "
+          f"{np.abs(pl - g['mov_planarity']).max():.2e}")
+    assert exact > 0.99
+    icp = sb.SimpleICP(verbose=False)
+    icp.add_point_clouds(pc_fix, pc_mov)
+    H, X_t, rbp, res = icp.run()
+    dH = np.linalg.norm(H - g["H"])
+    print(f"class run with movable normals: |dH|_F = {dH:.3e}, {len(res)} residuals vs {len(g['residuals'])}")
+    assert dH < 1e-5
+    assert abs(len(res) - len(g["residuals"])) <= 2
+    # without the movable columns the same clouds keep more correspondences
+    H0, _, _, res0 = sb.simpleicp(X_fix, X_mov)
+    assert len(res0) >= len(res)
+
+
+@pytest.mark.parametrize("max_angle", [5.0, 20.0, 90.0])
+def test_angle_between_normals_rejection(gpu, max_angle):
+    """The step the reference only declares: against the oracle's definition (applied after the
+    distance rejection, |n_fix . R n_mov| >= cos(max angle)); 90 degrees is the plain movable-
+    planarity run."""
+    g = load_golden("dragon_movnormals")
+    X_fix, X_mov = load_pair("dragon_movnormals")
+    nrm = full_normals(g, X_fix.shape[0])
+    tr = O.Trace()
+    H_o, _, x_o, sig_o, res_o = O.simpleicp(
+        X_fix, X_mov, normals=(g["normals"], g["planarity"]), mov_normals=(g["mov_normals"], g["mov_planarity"]),
+        max_angle_between_normals=max_angle, trace=tr)
+    with _capi.Engine() as e:
+        # first iteration stage by stage: mask equality
+        e.set_clouds(X_fix, X_mov)
+        e.set_mov_normals(*_mov_attr(g), max_angle_deg=max_angle)
+        e.set_selected(g["idx_sel"])
+        e.set_normals(*[a[g["idx_sel"]] for a in nrm])
+        e.match(np.eye(4))
+        keep = e.reject(0.3)[0]
+        assert np.array_equal(keep.astype(bool), tr.iterations[0].keep)
+        res = sb.register(X_fix, X_mov, normals=nrm, mov_normals=_mov_attr(g),
+                          max_angle_between_normals=max_angle, engine=e)
+    kept = [r["n_kept"] for r in res.records]
+    ref_kept = [int(it.keep.sum()) for it in tr.iterations]
+    dH = np.linalg.norm(res.H - H_o)
+    print(f"angle <= {max_angle}: |dH|_F = {dH:.3e}, kept {kept} vs {ref_kept}")
+    assert kept == ref_kept
+    assert dH < 1e-9
+    if max_angle == 90.0:
+        assert kept == [int(k.sum()) for k in g["it_keep"]]
+    else:
+        assert kept[0] < int(g["it_keep"][0].sum())
+    with pytest.raises(sb.SimpleICPException, match="needs the normals of the movable"):
+        sb.simpleicp(X_fix, X_mov, max_angle_between_normals=10.0)

@@ -31,6 +31,49 @@ def test_oracle_reproduces_reference(name):
     np.testing.assert_allclose(X_t[:64], g["X_mov_t_head"], rtol=0, atol=1e-12)
 
 
+def test_oracle_movable_side_planarity():
+    """pc_mov with normal columns: the second branch of CorrPts.reject_wrt_planarity
+    (corrpts.py:157-162), captured from the unmodified reference (make_golden.py config
+    dragon_movnormals).  Also pins estimate_normals on all 100 000 points of a cloud."""
+    g = load_golden("dragon_movnormals")
+    X_fix, X_mov = load_pair("dragon_movnormals")
+    tr = O.Trace()
+    mov = (g["mov_normals"], g["mov_planarity"])
+    H, X_t, x, sigma, res = O.simpleicp(X_fix, X_mov, trace=tr, mov_normals=mov, **g["kwargs"])
+    n = len(tr.iterations)
+    assert n == g["it_x"].shape[0]
+    for i in range(n):
+        assert np.array_equal(tr.iterations[i].pc2_idx, g["it_pc2_idx"][i])
+        assert np.array_equal(tr.iterations[i].keep, g["it_keep"][i])
+        np.testing.assert_allclose(tr.iterations[i].x, g["it_x"][i], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(H, g["H"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(res, g["residuals"], rtol=0, atol=1e-14)
+    # the filter did something: fewer correspondences than the plain dragon run keeps
+    assert g["it_keep"][0].sum() < load_golden("dragon")["it_keep"][0].sum()
+    # the restated estimate_normals reproduces the movable-side columns bit for bit
+    sub = np.arange(0, len(X_mov), 37)
+    nrm, plan, _ = O.estimate_normals(X_mov, sub, 10)
+    assert np.array_equal(nrm, g["mov_normals"][sub])
+    assert np.array_equal(plan, g["mov_planarity"][sub], equal_nan=True)
+
+
+def test_oracle_angle_rejection_extension():
+    """The angle test is an extension (the reference raises NotImplementedError): check its
+    definition on hand-made data, and that 90 degrees accepts everything."""
+    n1 = np.array([[0, 0, 1], [0, 0, 1], [0, 0, 1], [0, 0, 1]], dtype=np.float32)
+    n2 = np.array([[0, 0, -1], [0, np.sin(0.2), np.cos(0.2)], [1, 0, 0], [np.nan, 0, 0]], dtype=np.float32)
+    ok = O.angle_between_normals_ok(n1, n2, np.eye(4), 15.0)
+    assert ok.tolist() == [True, True, False, False]
+    Rz = np.eye(4)
+    Rz[:3, :3] = O.euler_angles_to_rotation_matrix(0.3, 0.0, 0.0)  # tilts n2 by 0.3 rad about x
+    assert O.angle_between_normals_ok(n1[:1], n2[:1], Rz, 15.0).tolist() == [False]
+    assert O.angle_between_normals_ok(n1[:3], n2[:3], np.eye(4), 90.0).all()
+    d = np.array([0.0, 0.1, -0.1, 0.05, 5.0])
+    pl = np.full(5, 0.9, dtype=np.float32)
+    keep, med, mad = O.reject(d, pl, 0.3, None, np.array([True, False, True, True, True]))
+    assert keep.tolist() == [True, False, True, True, False] and med == 0.05  # median/MAD still see entry 1
+
+
 def test_known_answer_readme_bunny():
     """python/README.md:62-65 prints the bunny H to 6 decimals (older release)."""
     g = load_golden("bunny")
