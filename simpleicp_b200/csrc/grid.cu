@@ -580,6 +580,7 @@ void grid_build_batch(Ctx& c, Batch& b, BatchGrid& bg, const std::vector<BatchHo
   const long long nsb = (total_cells + kScanItems - 1) / kScanItems;
   bg.block_sums.reserve(nsb + 1);
   c.misc_counters.reserve(64);
+  SICP_CUDA(cudaMemsetAsync(c.misc_counters.p + 16, 0, sizeof(unsigned int), st));  // the kernel's (unused here) occupancy counter
   k_scan_reduce<<<(unsigned)nsb, 256, 0, st>>>(bg.fill.p, total_cells, bg.block_sums.p, c.misc_counters.p + 16);
   k_scan_blocksums<<<1, 1024, 0, st>>>(bg.block_sums.p, (int)nsb);
   k_scan_down<<<(unsigned)nsb, 256, 0, st>>>(bg.fill.p, total_cells, bg.block_sums.p, bg.cell_table.p);
