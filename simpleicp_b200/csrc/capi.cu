@@ -90,6 +90,7 @@ void copy_any(Ctx& c, void* dst, const void* src, size_t bytes) {
 void sync(Ctx& c) { SICP_CUDA(cudaStreamSynchronize(c.stream)); }
 
 void init_state(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_loop) {
+  c.unresolved_clean = false;
   // small pageable H2D copies are staged by the runtime before the call returns
   DevState h;
   if (reset_loop) {
@@ -126,7 +127,7 @@ void require_normals(Ctx& c) {
 // iteration of this run left a predictor (it > 0), else the general cooperative kernel.
 void launch_iteration(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, int rec_slot,
                       bool allow_fused, bool want_sigma, cudaEvent_t mid = nullptr, cudaEvent_t after_match = nullptr) {
-  match_launch(c, true, nullptr, mid, c.expect_unresolved);
+  match_launch(c, true, nullptr, mid, c.expect_unresolved, -1.0, true);
   if (after_match) SICP_CUDA(cudaEventRecord(after_match, c.stream));
   // K <= 4096: one block owns the whole problem and falls back to the radix selection by itself
   // when there is no prediction (first iteration) — the barrier-free kernel serves every iteration
@@ -134,11 +135,13 @@ void launch_iteration(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, i
     rs_fused_launch(c, p, it, arm_stop, rec_slot, want_sigma);
   else
     reject_solve_launch(c, p, it, true, arm_stop, rec_slot);
+  c.unresolved_clean = true;  // both kernels reset the counter after reading it
 }
 
 // The fused kernel found its prediction unusable and parked the pipeline (state.stop == 3):
 // clear the flag so that the iteration can be repeated with the general kernel.
 void clear_stop_flag(Ctx& c) {
+  c.unresolved_clean = false;
   static const int zero = 0;
   SICP_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(c.dev_state.p) + offsetof(DevState, stop), &zero,
                             sizeof(int), cudaMemcpyHostToDevice, c.stream));
@@ -281,6 +284,7 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.fused = d.fused;
     c.warm_start = d.warm_start;
     c.sphere_scan = d.sphere_scan;
+    c.pdl = d.pdl;
     c.keep_knn = d.keep_knn;
     c.knn_coop = d.knn_coop;
   } else if (k == "nn_engine") {
@@ -304,6 +308,8 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.keep_knn = (value != 0) ? 1 : 0;
   } else if (k == "knn_coop") {
     c.knn_coop = (value < 0) ? -1 : ((value >= 2) ? 2 : ((value != 0) ? 1 : 0));
+  } else if (k == "pdl") {
+    c.pdl = (value != 0) ? 1 : 0;
   } else if (k == "sphere_scan") {
     c.sphere_scan = (value != 0) ? 1 : 0;
   } else if (k == "warm_start") {

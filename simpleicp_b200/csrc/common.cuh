@@ -225,6 +225,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+// Programmatic dependent launch (sm_90+).  A kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor in the stream is still running — once
+// every block of the predecessor has executed launch_dependents (or exited); it must not touch
+// anything the predecessor writes before pdl_wait(), which returns when the predecessor has
+// completed and its writes are visible.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ int cell_coord(double v, double o, double inv_h, int n) {
   int c = __double2int_rd((v - o) * inv_h);  // saturating
   return min(max(c, 0), n - 1);

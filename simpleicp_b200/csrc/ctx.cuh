@@ -105,6 +105,8 @@ struct Ctx {
   long long nn_pos_K = 0;
   int warm_start = 1;                // option "warm_start"
   int sphere_scan = 1;               // option "sphere_scan"
+  int pdl = 1;                       // option "pdl": programmatic dependent launch between the two kernels of an iteration
+  bool unresolved_clean = false;     // unresolved[K] is zero: the reject/solve kernel that read it last reset it
   DevBuf<double> resid;          // K, valid where keep
   DevBuf<double> resid_compact;  // kept order
   DevBuf<unsigned int> unresolved;  // query ids the grid could not bound + counter at [K]
@@ -235,8 +237,28 @@ void make_float4_copy(Ctx& c);
 // The transform is read from c.dev_state (T, Tinv) on the device.
 // allow_bf: bound the ring expansion by grid_max_rings and answer the rest with the brute-force
 // pass; otherwise the grid search runs to completion on its own (no extra launches).
+// in_loop: called from launch_iteration — the counter of unresolved queries was reset by the
+// previous iteration's reject/solve kernel (no memset between the kernels), and the kernel may be
+// launched programmatically dependent on it (option "pdl").
 void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid = nullptr,
-                  bool allow_bf = true, double cap2 = -1.0);
+                  bool allow_bf = true, double cap2 = -1.0, bool in_loop = false);
+
+// kernel launch, optionally with the programmatic-stream-serialization attribute (common.cuh: pdl_wait)
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                          bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SICP_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
 void set_state_transform(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_loop);
 void estimate_normals_launch(Ctx& c, int k);
 void reject_solve_launch(Ctx& c, const sicp_run_params& p, int it, bool do_solve, bool arm_stop,

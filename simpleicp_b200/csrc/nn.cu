@@ -249,10 +249,14 @@ __device__ __forceinline__ void match_coop_body(
     const CorrOut& co, const long long gt) {
   const long long qi = gt / MG;
   const int sub = threadIdx.x & (MG - 1);
-  if (qi >= K || st->stop) return;  // a whole group leaves together
+  pdl_launch_dependents();
+  if (qi >= K) return;  // a whole group leaves together
+  // the query's coordinates do not depend on the previous kernel: on their way before the wait
+  const double px = q_xyz[3 * qi + 0], py = q_xyz[3 * qi + 1], pz = q_xyz[3 * qi + 2];
+  pdl_wait();
+  if (st->stop) return;
   const unsigned int gmask = (MG == 32) ? 0xffffffffu : (((1u << MG) - 1u) << ((threadIdx.x & 31) & ~(MG - 1)));
   const Rigid Tinv = st->Tinv;
-  const double px = q_xyz[3 * qi + 0], py = q_xyz[3 * qi + 1], pz = q_xyz[3 * qi + 2];
   double qx, qy, qz;
   rigid_apply(Tinv, px, py, pz, qx, qy, qz);
   const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
@@ -798,6 +802,7 @@ constexpr size_t kBfSmem =
 }  // namespace
 
 void gather_queries_launch(Ctx& c) {
+  c.unresolved_clean = false;  // another K: the counter lives at another address
   c.q_xyz.reserve(3 * std::max<long long>(c.K, 1));
   k_gather_queries<<<(unsigned)((c.K + 255) / 256), 256, 0, c.stream>>>(c.fix_xyz.p, c.sel_idx.p,
                                                                        c.K, c.q_xyz.p);
@@ -921,7 +926,7 @@ void batch_match_launch(Ctx& c, Batch& b, bool warm) {
   c.tm.kernel_launches += 1;
 }
 
-void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, bool allow_bf, double cap2) {
+void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, bool allow_bf, double cap2, bool in_loop) {
   const long long K = c.K;
   // predictor histogram for the reject kernel: zero it if an earlier match filled it and no
   // reject consumed it (the reject kernel itself leaves it zeroed)
@@ -952,7 +957,10 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
     if (with_distance) c.lin_hist_pending = true;
     return;
   }
-  SICP_CUDA(cudaMemsetAsync(c.unresolved.p + K, 0, sizeof(unsigned int), c.stream));
+  if (!(in_loop && c.unresolved_clean))
+    SICP_CUDA(cudaMemsetAsync(c.unresolved.p + K, 0, sizeof(unsigned int), c.stream));
+  c.unresolved_clean = false;  // the caller's reject/solve launch declares it clean again
+  const bool pdl = in_loop && c.pdl;
   const bool use_bf = (c.nn_engine == SICP_NN_AUTO) && allow_bf;
   const int rmax = use_bf ? c.grid_max_rings : (1 << 30);
   if (c.match_group == 1) {
@@ -966,11 +974,10 @@ void match_launch(Ctx& c, bool with_distance, double* out_d2, cudaEvent_t mid, b
     if (mg == 0) mg = (K <= 16384) ? 16 : ((K <= 65536) ? 8 : 4);
     const long long threads = K * mg;
     const unsigned blocks = (unsigned)((threads + 127) / 128);
-#define SICP_LAUNCH_COOP(N)                                                                  \
-  k_match_grid_coop<N><<<blocks, 128, 0, c.stream>>>(c.gmov.view(), c.dev_state.p, c.q_xyz.p, \
-                                                    c.q_nrm.p, c.mov_xyz.p, K, rmax,          \
-                                                    with_distance ? 1 : 0, c.nn_idx.p, out,   \
-                                                    c.unresolved.p, lh, cap2, co)
+#define SICP_LAUNCH_COOP(N)                                                                          \
+  launch_kernel(k_match_grid_coop<N>, dim3(blocks), dim3(128), 0, c.stream, pdl, c.gmov.view(),       \
+                c.dev_state.p, c.q_xyz.p, c.q_nrm.p, c.mov_xyz.p, K, rmax, with_distance ? 1 : 0, \
+                c.nn_idx.p, out, c.unresolved.p, lh, cap2, co)
     if (mg == 2) SICP_LAUNCH_COOP(2);
     else if (mg == 4) SICP_LAUNCH_COOP(4);
     else if (mg == 8) SICP_LAUNCH_COOP(8);

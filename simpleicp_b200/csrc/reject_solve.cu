@@ -1179,6 +1179,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_reject_solve(RSArgs a, RSWork
         rec->distance_weight = w;
         rec->lm_iterations = lo.iters;
         rec->n_bruteforce = a.unresolved ? (int)a.unresolved[K] : 0;
+        if (a.unresolved) a.unresolved[K] = 0u;  // the next match starts from a clean counter
         st->n_kept = n_kept;
         st->skip = skip;
         st->w = w;
@@ -1568,6 +1569,8 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
   DevState* st = a.state;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long K = a.K;
+  pdl_launch_dependents();  // the next match may take the SMs this kernel's blocks leave early
+  pdl_wait();               // everything below reads what the match kernel wrote
   if (st->stop) return;  // a previous iteration met the stop rule (or asked for a re-run)
   RSF_STAMP(0);
 
@@ -1716,6 +1719,7 @@ __device__ void rs_fused_body(const RSArgs& a, RSWork wk, const int G, const int
   const unsigned int n_bf = a.unresolved ? __ldcg(&a.unresolved[K]) : 0u;
   if (tid == 0) {
     *wk.ticket = 0u;
+    if (a.unresolved) a.unresolved[K] = 0u;  // read above (n_bf): the next match starts from a clean counter
     wk.phase_t[4] = global_timer_ns();
     wk.phase_t[28] = 2;  // fused path
   }
@@ -2311,7 +2315,7 @@ void rs_fused_launch(Ctx& c, const sicp_run_params& p, int it, bool arm_stop, in
   wk.phase_t = c.phase_t.p;
   wk.lin_hist = c.lin_hist.p;
   wk.ticket = c.rsf_ticket.p;
-  k_rs_fused<<<G, RS_THREADS, sizeof(SharedF), c.stream>>>(a, wk);
+  launch_kernel(k_rs_fused, dim3(G), dim3(RS_THREADS), sizeof(SharedF), c.stream, c.pdl != 0, a, wk);
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 1;
 }

@@ -62,7 +62,7 @@ struct RSArgs {
   const double* mov_xyz;
   uint8_t* keep;
   double* resid;
-  const unsigned int* unresolved;
+  unsigned int* unresolved;  // [K] = queries the grid left to the brute-force pass; reset by the kernel after reading
   DevState* state;
   sicp_iter_record* rec;
   double min_planarity;  // compared against the float32 planarity promoted to float64
