@@ -683,11 +683,13 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
   int done = 0, fetched = 0, converged = 0, n_rerun = 0;
   std::vector<char> path((size_t)p->max_iterations, 0);  // 1: iteration served by the barrier-free kernel
   DevState h;
-  // host reads: after each of the first two iterations (they decide whether the brute-force
-  // pass is still needed), then every host_sync_every iterations; the device-side stop flag turns
-  // iterations queued past convergence into immediate returns
+  // host reads: after the second iteration (it tells whether the brute-force pass is still
+  // needed, and whether the first barrier-free iteration could use its prediction), then every
+  // host_sync_every iterations; the device-side stop flag turns iterations queued past
+  // convergence into immediate returns.  A read drains the pipeline (~25 us of idle GPU), an
+  // iteration queued in vain costs ~8 us.
   const int every = std::max(1, c.host_sync_every);
-  int next_sync = 0;
+  int next_sync = std::min(1, every - 1);
   int general_at = -1;  // iteration to repeat with the general kernel (fused prediction missed)
   c.expect_unresolved = true;
   for (int it = 0; it < p->max_iterations; ++it) {
@@ -696,7 +698,7 @@ static void run_loop(sicp_ctx* ctx, Ctx& c, const sicp_run_params* p, sicp_run_r
     path[(size_t)it] = fused ? 1 : 0;
     tr(fused ? "it (fused)" : "it (general)", it);
     if (it >= next_sync || it + 1 == p->max_iterations) {
-      next_sync = (it < 2) ? it + 1 : it + every;
+      next_sync = it + every;
       fetch_records(c, fetched, it + 1 - fetched);
       SICP_CUDA(cudaMemcpyAsync(&h, c.dev_state.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
       sync(c);

@@ -918,10 +918,13 @@ void batch_match_launch(Ctx& c, Batch& b, bool warm) {
   int mg = c.match_group;
   if (mg == 0 || mg == 1) mg = (total <= 16384) ? 16 : ((total <= 65536) ? 8 : 4);
   const dim3 grid((unsigned)((b.Kmax * mg + 127) / 128), b.n_pairs);
-  if (mg == 2) k_match_batch<2><<<grid, 128, 0, c.stream>>>(a);
-  else if (mg == 4) k_match_batch<4><<<grid, 128, 0, c.stream>>>(a);
-  else if (mg == 8) k_match_batch<8><<<grid, 128, 0, c.stream>>>(a);
-  else k_match_batch<16><<<grid, 128, 0, c.stream>>>(a);
+  // programmatically dependent on the previous iteration's k_rs_batch (both kernels wait before
+  // they touch anything the other writes; the pair descriptors are static)
+  const bool pdl = c.pdl != 0;
+  if (mg == 2) launch_kernel(k_match_batch<2>, grid, dim3(128), 0, c.stream, pdl, a);
+  else if (mg == 4) launch_kernel(k_match_batch<4>, grid, dim3(128), 0, c.stream, pdl, a);
+  else if (mg == 8) launch_kernel(k_match_batch<8>, grid, dim3(128), 0, c.stream, pdl, a);
+  else launch_kernel(k_match_batch<16>, grid, dim3(128), 0, c.stream, pdl, a);
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 1;
 }

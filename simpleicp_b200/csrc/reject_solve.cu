@@ -2358,7 +2358,7 @@ void batch_rs_launch(Ctx& c, Batch& b, const sicp_run_params& p, int it, bool wa
   ba.partials = b.partials.p;
   ba.ticket = b.ticket.p;
   ba.phase_t = b.phase_t.p;
-  k_rs_batch<<<b.n_pairs, RS_THREADS, sizeof(SharedF), c.stream>>>(ba);
+  launch_kernel(k_rs_batch, dim3(b.n_pairs), dim3(RS_THREADS), sizeof(SharedF), c.stream, c.pdl != 0, ba);
   SICP_CUDA(cudaGetLastError());
   c.tm.kernel_launches += 1;
 }
