@@ -282,14 +282,14 @@ __device__ __forceinline__ void match_coop_body(
   // the grid instead of rings expanding through empty space.  rs = radius of the cube of cells
   // already scanned around the query's cell (0: none).  Returns false (nothing done) when the box
   // is too large to be worth it: the bound is poor, another ring will improve it.
-  auto sphere_scan = [&](const int rs) -> bool {
+  auto sphere_scan = [&](const int rs, const int max_rows) -> bool {
     const double slack = 1e-9 * g.h;  // cell faces vs the floor() that assigned the points
     const double R = sqrt(best) * (1.0 + 1e-12) + slack;
     const int ya = cell_coord(qy - R, g.oy, g.inv_h, g.ny), yb = cell_coord(qy + R, g.oy, g.inv_h, g.ny);
     const int za = cell_coord(qz - R, g.oz, g.inv_h, g.nz), zb = cell_coord(qz + R, g.oz, g.inv_h, g.nz);
     const int nyb = yb - ya + 1;
     const long long rows = (long long)nyb * (zb - za + 1);
-    if (rows > 64 * MG) return false;  // ~15 instructions per pruned row: cheaper than the next rings up to here
+    if (rows > max_rows) return false;
     for (int t = sub; t < (int)rows; t += MG) {
       const int zz = za + t / nyb, yy = ya + t % nyb;
       const double ylo = g.oy + yy * g.h, zlo = g.oz + zz * g.h;
@@ -324,7 +324,12 @@ __device__ __forceinline__ void match_coop_body(
     return true;
   };
   const bool use_sphere = (cap2 < 0.0) && co.sphere;
-  if (use_sphere && best < kInf && sphere_scan(0)) resolved = true;
+  // Warm start: finish inside the sphere of the previous neighbour right away when that sphere
+  // is small (the steady state: 1-4 rows).  After a large update of the transform (second
+  // iteration of a registration) the old neighbour is a poor bound — several cells — while the
+  // true one is almost surely in the query's own row: ring 1 first, it prunes with the bound it
+  // has and leaves a much smaller sphere to the scan after it.
+  if (use_sphere && best < kInf && sphere_scan(0, 4 * MG)) resolved = true;
   for (int r = 1; !resolved; ++r) {
     const int x0 = cx - r, x1 = cx + r;
     const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
@@ -452,6 +457,12 @@ __device__ __forceinline__ void match_coop_body(
     // step): a surface at distance D crosses one of the axes within sqrt(3) D, the first point
     // found bounds the search, and the sphere scan below finishes it.
     if (use_sphere && r == 1 && best == kInf) {
+      // The y and z probes read three x-neighbouring cells (one contiguous record range, the same
+      // two cell-table loads): a sheet sampled at ~3 points per cell has holes, and a probe that
+      // slips through one runs on until another axis meets the surface ten times farther out —
+      // 5 % of the queries of the C3 pair, i.e. a third of the warps, with single-cell probes.
+      // The lanes only vote per step; the (distance, index, position) reduction runs once, after
+      // the step that found something.
       for (int s2 = 2; s2 <= 96; ++s2) {
         bool any_inside = false;
         for (int t = sub; t < 6; t += MG) {
@@ -459,28 +470,32 @@ __device__ __forceinline__ void match_coop_body(
           const int x = cx + (axis == 0 ? off : 0), y = cy + (axis == 1 ? off : 0), z = cz + (axis == 2 ? off : 0);
           if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
           any_inside = true;
-          const long long cell = ((long long)z * g.ny + y) * g.nx + x;
-          scan_range(g.recs, cs[cell], cs[cell + 1], qx, qy, qz, best, bidx, bpos);
+          const long long row = ((long long)z * g.ny + y) * g.nx;
+          const int xl = (axis == 0) ? x : max(x - 1, 0), xh = (axis == 0) ? x : min(x + 1, g.nx - 1);
+          scan_range(g.recs, cs[row + xl], cs[row + xh + 1], qx, qy, qz, best, bidx, bpos);
         }
-        unsigned int inside = any_inside ? 1u : 0u;
+        const bool found = __any_sync(gmask, best < kInf);
+        const bool inside = __any_sync(gmask, any_inside);
+        if (found) {
 #pragma unroll
-        for (int o = MG / 2; o > 0; o >>= 1) {
-          const double od = __shfl_xor_sync(gmask, best, o, MG);
-          const long long oi = __shfl_xor_sync(gmask, bidx, o, MG);
-          const uint32_t op = __shfl_xor_sync(gmask, bpos, o, MG);
-          inside |= __shfl_xor_sync(gmask, inside, o, MG);
-          if (od < best || (od == best && oi >= 0 && (bidx < 0 || oi < bidx))) {
-            best = od;
-            bidx = oi;
-            bpos = op;
+          for (int o = MG / 2; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(gmask, best, o, MG);
+            const long long oi = __shfl_xor_sync(gmask, bidx, o, MG);
+            const uint32_t op = __shfl_xor_sync(gmask, bpos, o, MG);
+            if (od < best || (od == best && oi >= 0 && (bidx < 0 || oi < bidx))) {
+              best = od;
+              bidx = oi;
+              bpos = op;
+            }
           }
+          break;
         }
-        if (best < kInf || !inside) break;
+        if (!inside) break;
       }
     }
     // a point is known now: finish inside its sphere instead of growing the cube ring by ring
     // (best is uniform across the group after the reduction, so the whole group takes one branch)
-    if (use_sphere && best < kInf && sphere_scan(r)) {
+    if (use_sphere && best < kInf && sphere_scan(r, 64 * MG)) {  // ~15 instructions per pruned row: cheaper than the next rings up to there
       resolved = true;
       break;
     }
