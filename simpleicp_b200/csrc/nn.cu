@@ -282,25 +282,47 @@ __device__ __forceinline__ void match_coop_body(
   // the grid instead of rings expanding through empty space.  rs = radius of the cube of cells
   // already scanned around the query's cell (0: none).  Returns false (nothing done) when the box
   // is too large to be worth it: the bound is poor, another ring will improve it.
+  // The row bounds are evaluated in float, in CELL units, with margins that keep every bound on
+  // the safe side (a row is only skipped / narrowed when it certainly holds nothing nearer than
+  // `best`); the distances themselves stay float64.  (Per-row float64 bounds, a float64 sqrt, two
+  // float64 floor conversions and an integer division were half of the first iteration's
+  // instructions, profiles/r2_README.md.)
+  const float fqx = (float)((qx - g.ox) * g.inv_h), fqy = (float)((qy - g.oy) * g.inv_h),
+              fqz = (float)((qz - g.oz) * g.inv_h);
+  // float32 error of a cell coordinate (a query may lie far outside the grid) + cell faces vs the
+  // floor() that assigned the points
+  const float marg = 1e-3f + 4e-7f * fmaxf(fmaxf(fabsf(fqx), fabsf(fqy)),
+                                           fmaxf(fabsf(fqz), (float)max(g.nx, max(g.ny, g.nz))));
+  const double inv_h2 = g.inv_h * g.inv_h;
   auto sphere_scan = [&](const int rs, const int max_rows) -> bool {
-    const double slack = 1e-9 * g.h;  // cell faces vs the floor() that assigned the points
-    const double R = sqrt(best) * (1.0 + 1e-12) + slack;
-    const int ya = cell_coord(qy - R, g.oy, g.inv_h, g.ny), yb = cell_coord(qy + R, g.oy, g.inv_h, g.ny);
-    const int za = cell_coord(qz - R, g.oz, g.inv_h, g.nz), zb = cell_coord(qz + R, g.oz, g.inv_h, g.nz);
+    const float Rc = sqrtf(__double2float_ru(best * inv_h2)) * (1.0f + 1e-6f) + marg;  // radius in cells, rounded up
+    const int ya = min(max(__float2int_rd(fqy - Rc), 0), g.ny - 1), yb = min(max(__float2int_rd(fqy + Rc), 0), g.ny - 1);
+    const int za = min(max(__float2int_rd(fqz - Rc), 0), g.nz - 1), zb = min(max(__float2int_rd(fqz + Rc), 0), g.nz - 1);
     const int nyb = yb - ya + 1;
     const long long rows = (long long)nyb * (zb - za + 1);
     if (rows > max_rows) return false;
-    for (int t = sub; t < (int)rows; t += MG) {
-      const int zz = za + t / nyb, yy = ya + t % nyb;
-      const double ylo = g.oy + yy * g.h, zlo = g.oz + zz * g.h;
-      const double by = fmax(fmax(ylo - qy, qy - (ylo + g.h)) - slack, 0.0);
-      const double bz = fmax(fmax(zlo - qz, qz - (zlo + g.h)) - slack, 0.0);
-      const double lb = by * by + bz * bz;
-      const double lim = best * (1.0 + 1e-12);  // strictly farther rows only: ties are still visited
-      if (lb > lim) continue;
-      const double xr = sqrt(lim - lb) * (1.0 + 1e-12) + slack;
-      const int xs = cell_coord(qx - xr, g.ox, g.inv_h, g.nx), xe = cell_coord(qx + xr, g.ox, g.inv_h, g.nx);
-      const long long row = ((long long)zz * g.ny + yy) * g.nx;
+    // (yr, zr) walk the box with stride MG, kept incrementally (no division per row)
+    int zr = sub / nyb, yr = sub - zr * nyb;
+    float limc = __double2float_ru(best * (1.0 + 1e-12) * inv_h2);  // strictly farther rows only: ties are still visited
+    double best_seen = best;
+    for (int t = sub; t < (int)rows; t += MG, yr += MG) {
+      while (yr >= nyb) {
+        yr -= nyb;
+        ++zr;
+      }
+      const int yy = ya + yr, zz = za + zr;
+      if (best != best_seen) {
+        best_seen = best;
+        limc = __double2float_ru(best * (1.0 + 1e-12) * inv_h2);
+      }
+      const float by = fmaxf(fabsf(fqy - ((float)yy + 0.5f)) - 0.5f - marg, 0.0f);
+      const float bz = fmaxf(fabsf(fqz - ((float)zz + 0.5f)) - 0.5f - marg, 0.0f);
+      const float lb = (by * by + bz * bz) * (1.0f - 1e-6f);  // rounded down
+      if (lb > limc) continue;
+      const float xr = sqrtf(limc - lb) * (1.0f + 1e-6f) + marg;
+      const int xs = max(__float2int_rd(fqx - xr), 0), xe = min(__float2int_rd(fqx + xr), g.nx - 1);
+      if (xs > xe) continue;  // the chord lies outside the grid
+      const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;  // < 2^25 cells
       if (rs > 0 && abs(yy - cy) <= rs && abs(zz - cz) <= rs) {
         // cells cx - rs .. cx + rs of this row were scanned by the rings
         const int le = min(xe, cx - rs - 1), rb = max(xs, cx + rs + 1);
