@@ -228,3 +228,52 @@ def test_cli_variant_cpp_prints_the_cpp_driver_output(gpu, tmp_path):
         np.testing.assert_allclose(sb.read_xyz(fo), O.transform_by_H(X_mov, ref.T), atol=2e-4)
     bad = subprocess.run([str(cli), "-f", str(f1), "-m", str(f2), "--variant", "nope"], capture_output=True, text=True)
     assert bad.returncode == 1 and "unknown variant" in bad.stderr
+
+
+def test_reference_cpp_cli_linked_against_the_library(gpu, tmp_path):
+    """INTEGRATION.md section 5 as a running program: the reference's own, unmodified CLI main()
+    (c++/src/simpleicp-cli.cpp) linked with integration/cpp/simpleicp_b200_binding.cpp -- the
+    reference's SimpleICP() signature implemented on the C ABI -- instead of its CPU sources
+    (oracle/Makefile -> oracle/_ref/simpleicp_cpp_b200, built where /root/reference exists).  Its
+    screen output must be the library's linearised run, and agree with the CPU build of the same
+    CLI (tests/golden/cppref_dragon.npz) as far as the eigenvector sign convention allows."""
+    import re
+    import subprocess
+
+    from conftest import GOLD, REPO
+
+    exe = REPO / "oracle" / "_ref" / "simpleicp_cpp_b200"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/simpleicp_cpp_b200 not built (needs the reference tree at build time)")
+    X_fix, X_mov = load_pair("dragon")
+    f1, f2 = tmp_path / "dragon1.xyz", tmp_path / "dragon2.xyz"
+    sb.write_xyz(f1, X_fix, decimals=4, header=False)
+    sb.write_xyz(f2, X_mov, decimals=4, header=False)
+    r = subprocess.run([str(exe), "--fixed", str(f1), "--movable", str(f2)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    ours = sb.simpleicp_linearized(X_fix, X_mov, compose="H*dH")
+    assert _tables_agree(r.stdout, ours.table)
+    pat = r"^\[\s*(-?[\d.]+)\s+(-?[\d.]+)\s+(-?[\d.]+)\s+(-?[\d.]+)\]$"
+    H = np.array(re.findall(pat, r.stdout, re.M), dtype=float)
+    assert np.abs(H - ours.H).max() < 1e-6                      # same library run, printed to 6 decimals
+    for line in ("Create point cloud objects ...", "Select points for correspondences in fixed point cloud ...",
+                 "Estimate normals of selected points ...", "Start iterations ...",
+                 "Convergence criteria fulfilled -> stop iteration!", "Estimated transformation matrix H:"):
+        assert line in r.stdout
+    assert re.search(r"^Finished in \d+\.\d{3} seconds!$", r.stdout, re.M)  # what scripts/benchmark.sh:45-51 parses
+    # against the CPU build of the same CLI: same registration, other eigenvector signs
+    g = dict(np.load(GOLD / "cppref_dragon.npz"))
+    shown = re.findall(r"^\s+(\d+) \|\s+(\d+) \|", r.stdout, re.M)
+    assert abs(len(shown) - (len(g["n_kept"]) - 1)) <= 1
+    assert np.abs(H - g["H_api"]).max() < 5e-3                   # H * dH depends on the path
+    T = np.eye(4)
+    for dH in g["dH"]:
+        T = dH @ T
+    assert np.abs(ours.T - T).max() < 1e-5                       # the applied transform does not
+    # the reference CLI's error path (simpleicp.cpp:26-36 caught at simpleicp-cli.cpp:60-64)
+    far = tmp_path / "far.xyz"
+    sb.write_xyz(far, X_mov + 1e4, decimals=4, header=False)
+    bad = subprocess.run([str(exe), "--fixed", str(f1), "--movable", str(far), "--max_overlap_distance", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert bad.returncode == 1
+    assert "Caught exception: Point clouds do not overlap within max_overlap_distance = 1.00000." in bad.stderr
