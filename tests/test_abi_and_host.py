@@ -148,6 +148,36 @@ def test_pointcloud_container():
         sb.PointCloud(X[:, :2], columns=["x", "y"])
 
 
+def test_sparse_normal_columns_equal_the_reference_construction():
+    """PointCloud.set_normals assembles the sparse float32 columns from (index, value) pairs; the
+    result must be the array the reference builds (pointcloud.py:200-203: SparseArray of a dense
+    NaN-filled column): same values, dtype, sparse index, and NaN values not stored."""
+    import pandas as pd
+
+    from simpleicp_b200.pointcloud import _sparse_f32_column
+
+    rng = np.random.default_rng(3)
+    n = 5000
+    for idx in (np.sort(rng.choice(n, 700, replace=False)), np.array([0]), np.array([n - 1]), np.arange(n),
+                rng.permutation(n)[:50], np.array([], dtype=np.int64)):  # unsorted / empty: dense route
+        vals = rng.standard_normal(idx.size).astype(np.float32)
+        if idx.size > 3:
+            vals[2] = np.nan  # a degenerate neighbourhood: NaN normal
+        col = np.full(n, np.nan, dtype=np.float32)
+        col[idx] = vals
+        ref = pd.arrays.SparseArray(col)
+        got = _sparse_f32_column(n, np.asarray(idx, dtype=np.int64), vals)
+        assert got.dtype == ref.dtype and str(got.dtype) == "Sparse[float32, nan]"
+        assert np.array_equal(np.asarray(got), np.asarray(ref), equal_nan=True)
+        assert got.sp_index.equals(ref.sp_index) and np.array_equal(got.sp_values, ref.sp_values)
+    pc = sb.PointCloud(rng.random((n, 3)), columns=["x", "y", "z"])
+    idx = np.arange(0, n, 7)
+    v = rng.random(idx.size).astype(np.float32)
+    pc.set_normals(idx, v, v, v, v)
+    assert pc["nx"].to_numpy()[7] == v[1] and np.isnan(pc["nz"].to_numpy()[8])
+    assert pc["planarity"].sparse.density == pytest.approx(idx.size / n)
+
+
 def test_argument_checks_match_reference_messages():
     X = np.zeros((10, 3))
     icp = sb.SimpleICP(verbose=False)
