@@ -89,8 +89,12 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value);
  *        reject + solve in the barrier-free kernel, 0: always the cooperative kernel),
  *        "warm_start" (1: the grid search of an iteration starts from the previous iteration's
  *        neighbour as upper bound), "keep_knn" (see sicp_get_knn), "knn_coop" (k-NN search: 1 cooperative
- *        lanes per query (k <= 16), 0 one thread per query, -1 (default) by the number of queries), "defaults" (any value: every option back
- *        to its default)                              */
+ *        lanes per query (k <= 16), 0 one thread per query, -1 (default) by the number of queries),
+ *        "upload_threads" (worker threads that stage a cloud given in PAGEABLE host memory --
+ *        e.g. a NumPy array -- through pinned buffers, default 2; 0: plain cudaMemcpyAsync, which
+ *        the driver stages on the calling thread; pinned and device sources never use them),
+ *        "upload_chunk_kb" (slice size of that staging, default 2048), "defaults" (any value:
+ *        every option back to its default)                              */
 
 /* ---- clouds: SimpleICP.add_point_clouds (simpleicp.py:58-73) + PointCloud.X ---------------- */
 int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz /*[h|d] n_fix x 3*/, int64_t n_fix,

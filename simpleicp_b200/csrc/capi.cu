@@ -89,6 +89,39 @@ void copy_any(Ctx& c, void* dst, const void* src, size_t bytes) {
 
 void sync(Ctx& c) { SICP_CUDA(cudaStreamSynchronize(c.stream)); }
 
+// A whole cloud, host -> device.  Pageable sources (NumPy arrays) take the threaded staging path
+// of upload.cuh; pinned / device sources are one cudaMemcpyAsync.
+constexpr size_t kThreadedUploadMin = 4u << 20;
+bool threaded_upload(Ctx& c, const void* src, size_t bytes) {
+  return c.upload_threads > 0 && bytes >= kThreadedUploadMin && PageableUploader::is_pageable(src);
+}
+// ... on the context's stream, complete (stream-ordered) when the call returns
+void upload_cloud(Ctx& c, void* dst, const void* src, size_t bytes) {
+  if (!threaded_upload(c, src, bytes)) {
+    copy_any(c, dst, src, bytes);
+    return;
+  }
+  SICP_CUDA(cudaEventRecord(c.ev_user, c.stream));
+  c.up.start(c.device, c.upload_threads, dst, src, bytes, c.ev_user);
+  c.up.finish(c.stream);
+}
+// ... in the background (copy stream or worker threads) after everything queued on the context's
+// stream so far; wait_background_upload() makes the context's stream wait for it
+void start_background_upload(Ctx& c, void* dst, const void* src, size_t bytes) {
+  SICP_CUDA(cudaEventRecord(c.ev_user, c.stream));
+  if (threaded_upload(c, src, bytes)) {
+    c.up.start(c.device, c.upload_threads, dst, src, bytes, c.ev_user);
+    return;
+  }
+  SICP_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_user, 0));
+  SICP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c.copy_stream));
+  SICP_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
+}
+void wait_background_upload(Ctx& c) {
+  if (c.up.active()) c.up.finish(c.stream);
+  else SICP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+}
+
 void init_state(Ctx& c, const double x[6], const Rigid* T_or_null, bool reset_loop) {
   c.unresolved_clean = false;
   // small pageable H2D copies are staged by the runtime before the call returns
@@ -174,12 +207,14 @@ using namespace sicp;
 #define API_END                                              \
   }                                                          \
   catch (const sicp::Error& e) {                             \
+    c.up.abandon();                                          \
     c.err = e.msg;                                           \
     sicp::set_thread_error(e.msg);                           \
     if (e.code == SICP_ERR_CUDA) cudaGetLastError();         \
     return e.code;                                           \
   }                                                          \
   catch (const std::exception& e) {                          \
+    c.up.abandon();                                          \
     c.err = e.what();                                        \
     sicp::set_thread_error(c.err);                           \
     return SICP_ERR_CUDA;                                    \
@@ -281,6 +316,8 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     c.rs_blocks = d.rs_blocks;
     c.match_group = d.match_group;
     c.host_sync_every = d.host_sync_every;
+    c.upload_threads = d.upload_threads;
+    c.up.chunk = d.up.chunk;
     c.fused = d.fused;
     c.warm_start = d.warm_start;
     c.sphere_scan = d.sphere_scan;
@@ -323,6 +360,13 @@ int32_t sicp_set_option(sicp_ctx* ctx, const char* key, double value) {
     SICP_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16, SICP_ERR_BAD_ARG,
                  "match_group must be 0 (auto), 1, 2, 4, 8 or 16");
     c.match_group = (int)value;
+  } else if (k == "upload_threads") {
+    SICP_REQUIRE(value >= 0 && value <= PageableUploader::kMaxThreads, SICP_ERR_BAD_ARG,
+                 "upload_threads must be within [0, 8]");
+    c.upload_threads = (int)value;
+  } else if (k == "upload_chunk_kb") {
+    SICP_REQUIRE(value >= 64 && value <= 4096, SICP_ERR_BAD_ARG, "upload_chunk_kb must be within [64, 4096]");
+    c.up.chunk = (size_t)value << 10;
   } else if (k == "host_sync_every") {
     SICP_REQUIRE(value >= 1 && value <= 1024, SICP_ERR_BAD_ARG, "host_sync_every out of range");
     c.host_sync_every = (int)value;
@@ -374,13 +418,10 @@ int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, con
     StageTimer t(c, &c.tm.upload_ms);
     c.fix_xyz.reserve(3 * n_fix);
     c.mov_xyz.reserve(3 * n_mov);
-    copy_any(c, c.mov_xyz.p, mov_xyz, sizeof(double) * 3 * n_mov);
+    upload_cloud(c, c.mov_xyz.p, mov_xyz, sizeof(double) * 3 * n_mov);
     t.stop();
   }
-  SICP_CUDA(cudaEventRecord(c.ev_user, c.stream));
-  SICP_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_user, 0));
-  SICP_CUDA(cudaMemcpyAsync(c.fix_xyz.p, fix_xyz, sizeof(double) * 3 * n_fix, cudaMemcpyDefault, c.copy_stream));
-  SICP_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
+  start_background_upload(c, c.fix_xyz.p, fix_xyz, sizeof(double) * 3 * n_fix);
   c.n_fix = n_fix;
   c.n_mov = n_mov;
   c.gfix.built = false;
@@ -390,7 +431,7 @@ int32_t sicp_set_clouds(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, con
     make_float4_copy(c);
     t.stop();
   }
-  SICP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+  wait_background_upload(c);
   SICP_CUDA(cudaStreamSynchronize(c.copy_stream));  // the caller may reuse fix_xyz after return
   c.K = 0;
   c.have_normals = false;
@@ -879,16 +920,13 @@ int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, const
   // (bbox read-back 0.46 ms instead of 0.03 ms, whether by memcpy or by a store to mapped memory).
   {
     StageTimer t(c, &c.tm.upload_ms);
-    copy_any(c, overlap ? c.mov_xyz.p : c.fix_xyz.p, overlap ? mov_xyz : fix_xyz,
-             sizeof(double) * 3 * (overlap ? n_mov : n_fix));
+    upload_cloud(c, overlap ? c.mov_xyz.p : c.fix_xyz.p, overlap ? mov_xyz : fix_xyz,
+                 sizeof(double) * 3 * (overlap ? n_mov : n_fix));
     t.stop();
   }
   auto queue_second_copy = [&]() {
-    SICP_CUDA(cudaEventRecord(c.ev_user, c.stream));
-    SICP_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_user, 0));
-    SICP_CUDA(cudaMemcpyAsync(overlap ? c.fix_xyz.p : c.mov_xyz.p, overlap ? fix_xyz : mov_xyz,
-                              sizeof(double) * 3 * (overlap ? n_fix : n_mov), cudaMemcpyDefault, c.copy_stream));
-    SICP_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
+    start_background_upload(c, overlap ? c.fix_xyz.p : c.mov_xyz.p, overlap ? fix_xyz : mov_xyz,
+                            sizeof(double) * 3 * (overlap ? n_fix : n_mov));
     tr("2nd copy queued");
   };
   auto build_mov = [&]() {
@@ -907,7 +945,7 @@ int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, const
   if (overlap) {
     build_mov();
     queue_second_copy();
-    SICP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+    wait_background_upload(c);
     // PointCloud.select_in_range on all fixed points (simpleicp.py:160-170), compacted on the host
     k_iota<<<(unsigned)((n_fix + 255) / 256), 256, 0, c.stream>>>(c.sel_idx.p, n_fix);
     c.K = n_fix;
@@ -963,7 +1001,7 @@ int32_t sicp_register(sicp_ctx* ctx, const double* fix_xyz, int64_t n_fix, const
   }
   tr("normals");
   if (!overlap) {
-    SICP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+    wait_background_upload(c);
     build_mov();
   }
   tr("mov grid");

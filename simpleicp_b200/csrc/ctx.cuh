@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "reject_solve.cuh"
+#include "upload.cuh"
 
 namespace sicp {
 
@@ -144,6 +145,8 @@ struct Ctx {
   double* scal_host = nullptr;           // pinned staging for small reads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t copy_stream = nullptr;   // second stream: fixed-cloud upload overlaps the movable grid build
+  PageableUploader up;                  // clouds in pageable host memory (NumPy arrays): threaded staging, upload.cuh
+  int upload_threads = 2;               // option "upload_threads": 0 = plain cudaMemcpyAsync for every source (measured: 2, 3, 4 threads alike, tools/upload_probe.py)
   cudaEvent_t ev_copy = nullptr, ev_user = nullptr;
   sicp_timings tm{};
 
