@@ -1,6 +1,9 @@
 """Diagnostics (GPU): why bench.py's e2e_simpleicp_pageable is above tools/upload_probe.py's number.
-Times simpleicp() on NumPy arrays with the library-owned engine and with an explicit one, before
-and after the process has run the CPU oracle (thread pools of SciPy / BLAS).  Not part of the product."""
+Times simpleicp() on NumPy arrays with the library-owned engine and with an explicit one, call by
+call, before and after the pinned end-to-end registrations bench.py runs first.  Result: 5.0-5.7 ms
+for the second to fourth call after an engine's creation, 4.7-5.0 ms from then on (the first call
+of a new engine costs 120-200 ms of allocations) -- bench.py now warms up twice and reports the
+median of five calls.  Not part of the product."""
 import sys
 import time
 from pathlib import Path
@@ -39,10 +42,3 @@ out = _capi.pinned_empty(X_mov.shape, np.float64)
 for _ in range(3):
     sb.register(Xf_p, Xm_p, correspondences=K, engine=eng, transform_out=out, want_normals=False)
 run("after pinned e2e      ")
-from oracle import simpleicp_oracle as O
-
-t0 = time.perf_counter()
-O.simpleicp(X_fix[:200000], X_mov[:200000], correspondences=2000, max_iterations=2)
-print(f"oracle call {time.perf_counter() - t0:.2f} s")
-run("after an oracle call  ")
-run("explicit, after oracle", engine=eng)
