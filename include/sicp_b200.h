@@ -58,19 +58,26 @@ typedef enum {
 } sicp_sign_mode;
 
 /* Algorithm variant of reject + solve (option key "variant").  The default is the Python package's
- * algorithm (the north-star path).  The linearised variants restate the C++/Rust/MATLAB/Julia
- * drivers (c++/src/corrpts.cpp:59-156, c++/src/simpleicp.cpp:54-80, rust/src/icp.rs:135-184):
- * median/MAD over ALL distances with the upper middle element (std::nth_element at n/2),
- * sigma = 1.4826 MAD, one linear solve A x = l per iteration, cloud moved by dH = H(euler(x), t),
- * residuals A x - l, sample standard deviation, no parameter uncertainties and no
- * observed/fixed parameters.  They differ in the matrix that is REPORTED: dH * H (the transform
- * really applied to the cloud; Rust rust/src/icp.rs:164, MATLAB matlab/simpleicp.m:55) or H * dH
- * (the C++ driver, c++/src/simpleicp.cpp:66).  Normals stay in the float32 storage of the
- * default variant (the C++ code keeps float64), see DESIGN.md.                                  */
+ * algorithm (the north-star path).  The linearised variants restate the C++ driver
+ * (c++/src/corrpts.cpp:59-156, c++/src/simpleicp.cpp:54-80; pinned to those sources, see
+ * tests/test_cpp_reference_pin.py): median/MAD over ALL distances with the upper middle element
+ * (std::nth_element at n/2), sigma = 1.4826 MAD, one linear solve A x = l per iteration, cloud
+ * moved by the RIGID dH = H(euler(x), t), residuals A x - l, sample standard deviation, no
+ * parameter uncertainties and no observed/fixed parameters.  They differ in the matrix that is
+ * REPORTED: H * dH (the C++ driver, c++/src/simpleicp.cpp:66) or dH * H, the transform really
+ * applied to the cloud and the composition order of the Rust / Julia / MATLAB drivers
+ * (rust/src/icp.rs:164, julia/simpleicp.jl:272, matlab/simpleicp.m:55).  Those three ports differ
+ * from the C++ arithmetic in two more points that are NOT reproduced: they move the cloud by the
+ * linearised matrix I + [x]_x itself (rust/src/icp.rs:339-344, matlab/simpleicp.m:146-152) -- not
+ * a rotation, so distances are not preserved and the search could not stay in the static grid
+ * of the untouched cloud -- and they average the two middle elements of an even-sized sample
+ * (rust/src/icp.rs:392-404).  Both effects are second order in the per-iteration angles.
+ * Normals stay in the float32 storage of the default variant (the C++ code keeps float64), see
+ * DESIGN.md.                                                                                    */
 typedef enum {
   SICP_VARIANT_PYTHON = 0,
-  SICP_VARIANT_LINEARIZED = 1,        /* reports dH * H                                          */
-  SICP_VARIANT_LINEARIZED_CPP = 2     /* reports H * dH                                          */
+  SICP_VARIANT_LINEARIZED = 1,        /* C++ arithmetic, reports dH * H                          */
+  SICP_VARIANT_LINEARIZED_CPP = 2     /* C++ arithmetic, reports H * dH (the C++ driver itself)  */
 } sicp_variant;
 
 /* ---- life cycle --------------------------------------------------------------------------- */

@@ -1,4 +1,5 @@
-"""CPU oracle for the LINEARISED simpleICP variant (the C++ / Rust / MATLAB / Julia semantics).
+"""CPU oracle for the LINEARISED simpleICP variant: the C++ driver's algorithm (the Rust / Julia /
+MATLAB ports share its structure; where they differ is listed below).
 
 TEST INFRASTRUCTURE ONLY (same rule as simpleicp_oracle.py: only tests/, smoke() and bench.py's
 CPU legs may import it; the product package never does).
@@ -18,7 +19,13 @@ source lines each function follows (paths relative to /root/reference/c++/src/):
 Composition of the reported matrix: the C++ driver accumulates ``H_new = H_old * dH``
 (simpleicp.cpp:66) while the Rust and MATLAB drivers accumulate ``dH * H`` (rust/src/icp.rs:164,
 matlab/simpleicp.m:55).  Both are offered (``compose="post"`` is the C++ one); the cloud itself is
-always moved by dH on the left, as all of them do.
+always moved by dH on the left, as all of them do.  Beyond the composition order the Rust, Julia
+and MATLAB ports (a) build dH from the linearised matrix I + [x]_x instead of the Euler product
+(rust/src/icp.rs:339-344, julia/simpleicp.jl:162-178, matlab/simpleicp.m:140-152) -- the
+``rotation="small_angle"`` switch below -- and (b) average the two middle elements of an
+even-sized sample in median / MAD (rust/src/icp.rs:392-409) where the C++ takes the upper one.
+Neither the product's linearised variants nor the default settings of this file reproduce (a)
+or (b): they follow the C++ sources, which is what can be compiled and pinned here.
 
 Parity status: PINNED to the reference's own C++ sources, modulo their three third-party
 libraries.  oracle/Makefile compiles the UNMODIFIED /root/reference/c++/src/{simpleicp,pointcloud,

@@ -1,4 +1,6 @@
-"""Linearised simpleICP variant on the GPU: the algorithm of the C++ / Rust / MATLAB / Julia drivers.
+"""Linearised simpleICP variant on the GPU: the algorithm of the C++ driver (and, up to two
+second-order details listed in include/sicp_b200.h next to ``sicp_variant``, of its Rust / Julia /
+MATLAB siblings, whose composition order ``dH * H`` is the default here).
 
 Mirror of the C++ entry point ``SimpleICP(X_fix, X_mov, correspondences, neighbors, min_planarity,
 max_overlap_distance, min_change, max_iterations)`` (/root/reference/c++/src/simpleicp.h,
@@ -32,7 +34,7 @@ from . import _capi
 
 _log = logging.getLogger(__name__)
 
-VARIANT_LINEARIZED = 1       # reports dH * H  (Rust rust/src/icp.rs:164, MATLAB simpleicp.m:55)
+VARIANT_LINEARIZED = 1       # C++ arithmetic, reports dH * H (composition order of rust/src/icp.rs:164, matlab/simpleicp.m:55)
 VARIANT_LINEARIZED_CPP = 2   # reports H * dH  (C++ simpleicp.cpp:66)
 
 
