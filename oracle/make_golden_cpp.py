@@ -40,7 +40,7 @@ OUT = REPO / "oracle" / "_ref"
 sys.path.insert(0, str(REPO / "tests"))
 
 # name -> (fixed, movable, CLI flags).  The first four are c++/run_simpleicp.sh:11-41 verbatim;
-# the last two add a non-default correspondences / neighbors / min_planarity combination and the
+# the next two add a non-default correspondences / neighbors / min_planarity combination and the
 # max_iterations exit (no convergence message).
 CONFIGS = {
     "dragon": ("dragon1.xyz", "dragon2.xyz", {}),
@@ -50,6 +50,11 @@ CONFIGS = {
     "dragon_k5000": ("dragon1.xyz", "dragon2.xyz",
                      {"correspondences": 5000, "neighbors": 15, "min_planarity": 0.5, "min_change": 0.1}),
     "bunny_maxit3": ("bunny_part1.xyz", "bunny_part2.xyz", {"max_overlap_distance": 1, "max_iterations": 3}),
+    # a small pair of the Python test file (python/simpleicp/tests/test_simpleicp.py:66-80) with the flag
+    # the C++ CLI has for it: fewer selectable points than correspondences (SelectNPts is a no-op), 32
+    # iterations.  (webots without its initial transform -- the C++ CLI has no such flag -- stays at
+    # the identity on a lattice full of equidistant neighbours: not kept.)
+    "multisensor": ("multisensor_lidar.xyz", "multisensor_radar.xyz", {"max_overlap_distance": 1}),
 }
 DEFAULTS = dict(correspondences=1000, neighbors=10, min_planarity=0.3, max_overlap_distance=-1.0,
                 min_change=1.0, max_iterations=100)  # c++/src/simpleicp-cli.cpp:20-35

@@ -35,7 +35,7 @@ import linearized_oracle as lo  # noqa: E402
 
 GOLD = ROOT / "tests" / "golden"
 DATA = {"dragon_k5000": "dragon", "bunny_maxit3": "bunny"}
-NAMES = ["dragon", "bunny", "airborne", "terrestrial", "dragon_k5000", "bunny_maxit3"]
+NAMES = ["dragon", "bunny", "airborne", "terrestrial", "dragon_k5000", "bunny_maxit3", "multisensor"]
 
 
 def load_cppref(name):
