@@ -16,7 +16,9 @@ from bench import make_pair
 n, K = 1_000_000, 100_000
 X_fix, X_mov, _ = make_pair(n, 0)
 from simpleicp_b200 import _capi
-import simpleicp_b200.simpleicp as drv
+import importlib
+
+drv = importlib.import_module("simpleicp_b200.simpleicp")  # the module (the package attribute of that name is the function)
 
 eng = _capi.Engine()
 drv.default_engine = lambda device=None: eng  # calls without engine= use this one, options kept
