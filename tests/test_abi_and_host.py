@@ -319,3 +319,31 @@ def test_angle_rejection_needs_movable_normals():
         sb.simpleicp(X, X, max_angle_between_normals=10.0)
     with pytest.raises(sb.SimpleICPException, match=r"within \[0, 90\]"):
         sb.simpleicp(X, X, mov_normals=(X[:, 0],) * 4, max_angle_between_normals=120.0)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside the product arm): ONE JSON
+    line on stdout with the contract's keys, the workload string of the product arm, the e2e and
+    cpu_baseline objects of the tier's reference arm.  Small sizes: the line, not the number."""
+    import json
+    import subprocess
+
+    import bench
+
+    r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--points", "20000", "--correspondences", "2000"], capture_output=True, text=True,
+                       timeout=600, cwd=str(REPO))
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1                                   # stdout is the JSON line and nothing else
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["metric"].startswith("correspondences/sec") and d["unit"] == "corr/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["config"]["workload"] == bench.workload_string(20000, 2000)   # same string as the product arm
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0 and e["value"] > 0 and e["unit"] == "corr/s"
